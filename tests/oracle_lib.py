@@ -1,0 +1,206 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs.
+The product package (gtsam_points_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+
+LINEARIZED_DOUBLES = 122
+
+
+def build(force=False):
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, dp, ip, lp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        L.orc_cloud_create.restype = vp
+        L.orc_cloud_create.argtypes = [dp, dp, C.c_size_t]
+        L.orc_cloud_destroy.argtypes = [vp]
+        L.orc_voxelmap_create.restype = vp
+        L.orc_voxelmap_create.argtypes = [C.c_double]
+        L.orc_voxelmap_destroy.argtypes = [vp]
+        L.orc_voxelmap_set_lru.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_voxelmap_insert.argtypes = [vp, vp]
+        L.orc_voxelmap_num_voxels.restype = C.c_size_t
+        L.orc_voxelmap_num_voxels.argtypes = [vp]
+        L.orc_voxelmap_export.argtypes = [vp, ip, dp, dp, ip]
+        L.orc_voxelmap_lookup.argtypes = [vp, dp, C.c_size_t, ip]
+        L.orc_kdtree_create.restype = vp
+        L.orc_kdtree_create.argtypes = [vp, C.c_int]
+        L.orc_kdtree_destroy.argtypes = [vp]
+        L.orc_kdtree_num_nodes.restype = C.c_size_t
+        L.orc_kdtree_num_nodes.argtypes = [vp]
+        L.orc_kdtree_knn.argtypes = [vp, dp, C.c_size_t, C.c_int, C.c_double, C.POINTER(C.c_uint64), dp, ip, C.c_int]
+        L.orc_vgicp_create.restype = vp
+        L.orc_vgicp_create.argtypes = [vp, vp]
+        L.orc_gicp_create.restype = vp
+        L.orc_gicp_create.argtypes = [vp, vp, vp]
+        L.orc_factor_destroy.argtypes = [vp]
+        L.orc_factor_set_num_threads.argtypes = [vp, C.c_int]
+        L.orc_factor_set_max_correspondence_distance.argtypes = [vp, C.c_double]
+        L.orc_factor_linearize.argtypes = [vp, dp, dp]
+        L.orc_factor_error.restype = C.c_double
+        L.orc_factor_error.argtypes = [vp, dp]
+        L.orc_factor_correspondences.argtypes = [vp, lp]
+        L.orc_calc_delta.argtypes = [dp, dp, dp]
+        L.orc_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def unpack_linearized(buf):
+    buf = np.asarray(buf, dtype=np.float64)
+    return dict(
+        H_target=buf[0:36].reshape(6, 6).copy(),
+        H_source=buf[36:72].reshape(6, 6).copy(),
+        H_target_source=buf[72:108].reshape(6, 6).copy(),
+        b_target=buf[108:114].copy(),
+        b_source=buf[114:120].copy(),
+        error=float(buf[120]),
+        num_inliers=int(buf[121]),
+    )
+
+
+class Cloud:
+    def __init__(self, pts, covs=None):
+        self.pts = np.ascontiguousarray(pts, dtype=np.float64)
+        self.covs = None if covs is None else np.ascontiguousarray(covs, dtype=np.float64).reshape(len(pts), 9)
+        self.n = len(self.pts)
+        self.h = lib().orc_cloud_create(_dp(self.pts), None if self.covs is None else _dp(self.covs), self.n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_cloud_destroy(self.h)
+            self.h = None
+
+
+class VoxelMap:
+    def __init__(self, resolution):
+        self.resolution = resolution
+        self.h = lib().orc_voxelmap_create(resolution)
+        self._clouds = []
+
+    def insert(self, cloud: Cloud):
+        lib().orc_voxelmap_insert(self.h, cloud.h)
+
+    @property
+    def num_voxels(self):
+        return lib().orc_voxelmap_num_voxels(self.h)
+
+    def export(self):
+        V = self.num_voxels
+        coords = np.zeros((V, 3), dtype=np.int32)
+        means = np.zeros((V, 3))
+        covs = np.zeros((V, 3, 3))
+        n = np.zeros(V, dtype=np.int32)
+        lib().orc_voxelmap_export(self.h, coords.ctypes.data_as(C.POINTER(C.c_int32)), _dp(means), _dp(covs), n.ctypes.data_as(C.POINTER(C.c_int32)))
+        return dict(coords=coords, means=means, covs=covs, n=n, resolution=self.resolution)
+
+    def lookup(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        out = np.zeros(len(xyz), dtype=np.int32)
+        lib().orc_voxelmap_lookup(self.h, _dp(xyz), len(xyz), out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_voxelmap_destroy(self.h)
+            self.h = None
+
+
+class KdTree:
+    def __init__(self, cloud: Cloud, num_threads=1):
+        self.cloud = cloud
+        self.h = lib().orc_kdtree_create(cloud.h, num_threads)
+
+    @property
+    def num_nodes(self):
+        return lib().orc_kdtree_num_nodes(self.h)
+
+    def knn(self, queries, k, max_sq_dist=np.finfo(np.float64).max, num_threads=1):
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        idx = np.zeros((len(q), k), dtype=np.uint64)
+        sqd = np.zeros((len(q), k))
+        found = np.zeros(len(q), dtype=np.int32)
+        lib().orc_kdtree_knn(
+            self.h, _dp(q), len(q), k, max_sq_dist, idx.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(sqd), found.ctypes.data_as(C.POINTER(C.c_int32)), num_threads
+        )
+        return idx.view(np.int64), sqd, found
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_kdtree_destroy(self.h)
+            self.h = None
+
+
+class Factor:
+    """IntegratedVGICPFactor (target = VoxelMap) or IntegratedGICPFactor (target = Cloud + KdTree)."""
+
+    def __init__(self, target, source: Cloud, tree: KdTree = None, num_threads=1):
+        self.target, self.source, self.tree = target, source, tree
+        if isinstance(target, VoxelMap):
+            self.h = lib().orc_vgicp_create(target.h, source.h)
+        else:
+            self.h = lib().orc_gicp_create(target.h, tree.h, source.h)
+        lib().orc_factor_set_num_threads(self.h, num_threads)
+
+    def set_num_threads(self, n):
+        lib().orc_factor_set_num_threads(self.h, n)
+
+    def set_max_correspondence_distance(self, d):
+        lib().orc_factor_set_max_correspondence_distance(self.h, d)
+
+    def linearize_raw(self, delta):
+        d = np.ascontiguousarray(delta, dtype=np.float64).reshape(16)
+        out = np.zeros(LINEARIZED_DOUBLES)
+        lib().orc_factor_linearize(self.h, _dp(d), _dp(out))
+        return out
+
+    def linearize(self, delta):
+        return unpack_linearized(self.linearize_raw(delta))
+
+    def error(self, delta):
+        d = np.ascontiguousarray(delta, dtype=np.float64).reshape(16)
+        return lib().orc_factor_error(self.h, _dp(d))
+
+    def correspondences(self):
+        out = np.zeros(self.source.n, dtype=np.int64)
+        lib().orc_factor_correspondences(self.h, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_factor_destroy(self.h)
+            self.h = None
+
+
+def calc_delta(T_target, T_source):
+    a = np.ascontiguousarray(T_target, dtype=np.float64).reshape(16)
+    b = np.ascontiguousarray(T_source, dtype=np.float64).reshape(16)
+    d = np.zeros(16)
+    lib().orc_calc_delta(_dp(a), _dp(b), _dp(d))
+    return d.reshape(4, 4)
+
+
+def max_threads():
+    return lib().orc_max_threads()
