@@ -1,0 +1,840 @@
+// b2_factors.cu -- the hot path: fused correspondence search + linearization of VGICP / GICP factors.
+//
+// Replaces, in ONE persistent kernel per (factor kind, storage type) group of a factor set:
+//   * IntegratedVGICPFactor_::update_correspondences + ::evaluate  (reference: include/gtsam_points/factors/impl/
+//     integrated_vgicp_factor_impl.hpp:99-172, :175-257), IntegratedGICPFactor_ likewise (impl/integrated_gicp_factor_impl.hpp:132-296),
+//   * scan_matching_reduce_omp (impl/scan_matching_reduction.hpp:16-68),
+//   * the reference's GPU twin: lookup_voxels_kernel / vgicp_derivatives_kernel / cub::DeviceReduce of LinearizedSystem6
+//     (include/gtsam_points/cuda/kernels/*.cuh, src/gtsam_points/factors/integrated_vgicp_derivatives_linearize.cu:23-55),
+//   * NonlinearFactorSetGPU's per-factor issue/sync loop (src/gtsam_points/cuda/nonlinear_factor_set_gpu.cpp:64-218).
+//
+// Design (B200-first):
+//   * float64 arithmetic end to end (pose * point and the voxel floor use individually rounded operations so that
+//     correspondence indices are bit-identical to the CPU float64 path); storage may be float32 where that is lossless.
+//   * per correspondence only A' = J'^T M J' (21 unique), c' = J'^T M r (6) and e are accumulated, with
+//     J' = [-hat(R p) | I]; since J_target = J' X and J_source = -J' D with X = [[I,0],[-hat(t),I]], D = diag(R,R),
+//     the five reference blocks are recovered once per factor: H_t = X^T A' X, H_s = D^T A' D, H_ts = -X^T A' D,
+//     b_t = X^T c', b_s = -D^T c'.  (~170 DFMA-class instructions per correspondence instead of ~1000.)
+//   * accumulators live in registers across a CTA's whole tile sequence; one transposing butterfly reduction
+//     (31 shuffles for 32 values) per CTA and factor; partial sums go to fixed slots and the last CTA of a factor
+//     reduces the slots in slot order => results are bit-reproducible run to run.
+//   * all factors of a set are covered by one launch: the grid walks a tile list (tile -> factor), CTA c takes tiles
+//     c, c+G, c+2G, ... so work is balanced and every CTA meets each factor in one contiguous run.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "b2_device.cuh"
+#include "b2_kdtree.cuh"
+
+namespace b2 {
+
+constexpr int kThreads = 256;
+constexpr int kPointsPerThread = 2;
+constexpr int kTile = kThreads * kPointsPerThread;
+constexpr int kAcc = 32;     // accumulator slots per partial record (29 used)
+constexpr int kMinBlocksPerSM = 2;
+
+enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
+
+struct FactorDesc {
+  const void* pts;    // 3 planes of n_pad
+  const void* covs;   // 6 planes of n_pad
+  uint32_t n;
+  uint32_t n_pad;
+  // VGICP target
+  const VoxelBucket* buckets;
+  uint32_t bucket_mask;
+  uint32_t pad0;
+  double inv_leaf;
+  // GICP target
+  const KdNodeGPU* nodes;
+  const double* leaf_pts;
+  uint32_t leaf_n_pad;
+  uint32_t pad1;
+  double max_sq;
+  // mean(3) | cov(6) | count records: voxels (id order) or target points (leaf order)
+  const double* records;
+  int32_t* corr;
+  uint32_t tile_begin;
+  uint32_t num_tiles;
+  uint32_t slot_begin[2];  // per mode
+  uint32_t num_slots[2];   // per mode
+  uint32_t out_index;      // index of the factor in its set (pose / result / counter)
+  uint32_t pad2;
+};
+
+__device__ __forceinline__ double ldv(const float* p, size_t i) { return static_cast<double>(__ldg(p + i)); }
+__device__ __forceinline__ double ldv(const double* p, size_t i) { return __ldg(p + i); }
+
+template <int OFF>
+__device__ __forceinline__ void bfly_step(double (&v)[kAcc], int lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int k = 0; k < OFF; k++) {
+    const double send = upper ? v[k] : v[k + OFF];
+    const double keep = upper ? v[k + OFF] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+
+// Transposing butterfly: 32 values per lane in, lane l ends up holding the warp total of value l (31 shuffles, fixed order).
+__device__ __forceinline__ double warp_reduce32(double (&v)[kAcc], int lane) {
+  bfly_step<16>(v, lane);
+  bfly_step<8>(v, lane);
+  bfly_step<4>(v, lane);
+  bfly_step<2>(v, lane);
+  bfly_step<1>(v, lane);
+  return v[0];
+}
+
+__device__ __forceinline__ int sym_idx(int i, int j) {
+  if (i > j) {
+    const int t = i;
+    i = j;
+    j = t;
+  }
+  return i * 3 - (i * (i - 1)) / 2 + (j - i);
+}
+
+// accumulator layout: 0..5 A_rr (upper), 6..14 A_rt (row-major, rows = rotation), 15..20 A_tt (upper), 21..23 c_r, 24..26 c_t, 27 error, 28 count
+struct Shared {
+  FactorDesc desc;
+  double red[kThreads / 32][kAcc];
+  double tot[kAcc];
+  double A[36], X[36], D[36];
+  double R[9], t[3];
+  int flag;
+};
+
+template <int MODE>
+__device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], const double (&Rr)[9], const double (&tr)[3], double* __restrict__ partials,
+                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double w = warp_reduce32(v, lane);
+  sh.red[warp][lane] = w;
+  if (tid == 0) {
+    // the pose lives in registers (static indices only); the epilogue indexes it dynamically, so stage it in shared memory
+#pragma unroll
+    for (int k = 0; k < 9; k++) sh.R[k] = Rr[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) sh.t[k] = tr[k];
+  }
+  const double* R = sh.R;
+  const double* t = sh.t;
+  __syncthreads();
+  const FactorDesc& d = sh.desc;
+  const uint32_t c = blockIdx.x;
+  const uint32_t slot = (c + G - (d.tile_begin % G)) % G;
+  if (warp == 0) {
+    double s = sh.red[0][lane];
+#pragma unroll
+    for (int k = 1; k < kThreads / 32; k++) s += sh.red[k][lane];
+    partials[(static_cast<size_t>(d.slot_begin[MODE]) + slot) * kAcc + lane] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&counters[d.out_index], 1u);
+    sh.flag = (prev == d.num_slots[MODE] - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!sh.flag) return;
+
+  // ---- last CTA of this factor: ordered reduction over the slots, then the per-factor epilogue ----
+  __threadfence();
+  {
+    const int k = lane, part = warp;
+    double s = 0.0;
+    for (uint32_t sl = part; sl < d.num_slots[MODE]; sl += kThreads / 32) s += __ldcg(&partials[(static_cast<size_t>(d.slot_begin[MODE]) + sl) * kAcc + k]);
+    sh.red[part][k] = s;
+  }
+  __syncthreads();
+  if (tid < kAcc) {
+    double s = sh.red[0][tid];
+#pragma unroll
+    for (int k = 1; k < kThreads / 32; k++) s += sh.red[k][tid];
+    sh.tot[tid] = s;
+  }
+  if (tid == 0) counters[d.out_index] = 0u;  // re-arm for the next launch
+  __syncthreads();
+
+  if (MODE == MODE_ERROR) {
+    if (tid == 0) out[d.out_index] = sh.tot[27];
+    __syncthreads();
+    return;
+  }
+
+  double* rec = out + static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES;
+  if (tid < 36) {
+    const int i = tid / 6, j = tid % 6;
+    // A' (symmetric 6x6), tangent order [rot, trans]
+    double a;
+    if (i < 3 && j < 3)
+      a = sh.tot[sym_idx(i, j)];
+    else if (i < 3)
+      a = sh.tot[6 + i * 3 + (j - 3)];
+    else if (j < 3)
+      a = sh.tot[6 + j * 3 + (i - 3)];
+    else
+      a = sh.tot[15 + sym_idx(i - 3, j - 3)];
+    sh.A[tid] = a;
+    // X = [[I, 0], [-hat(t), I]]
+    double x = (i == j) ? 1.0 : 0.0;
+    if (i >= 3 && j < 3) {
+      const int r = i - 3, cc = j;
+      // -hat(t) = [[0, t2, -t1], [-t2, 0, t0], [t1, -t0, 0]]
+      if (r == 0 && cc == 1) x = t[2];
+      if (r == 0 && cc == 2) x = -t[1];
+      if (r == 1 && cc == 0) x = -t[2];
+      if (r == 1 && cc == 2) x = t[0];
+      if (r == 2 && cc == 0) x = t[1];
+      if (r == 2 && cc == 1) x = -t[0];
+    }
+    sh.X[tid] = x;
+    // D = diag(R, R)
+    sh.D[tid] = ((i < 3) == (j < 3)) ? R[(i % 3) * 3 + (j % 3)] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 36) {
+    const int i = tid / 6, j = tid % 6;
+    double ht = 0.0, hs = 0.0, hts = 0.0;
+    for (int a = 0; a < 6; a++) {
+      double xa = 0.0, da = 0.0, xd = 0.0;  // (A X)[a][j], (A D)[a][j]
+      for (int b = 0; b < 6; b++) {
+        xa += sh.A[a * 6 + b] * sh.X[b * 6 + j];
+        da += sh.A[a * 6 + b] * sh.D[b * 6 + j];
+      }
+      xd = da;
+      ht += sh.X[a * 6 + i] * xa;
+      hs += sh.D[a * 6 + i] * da;
+      hts -= sh.X[a * 6 + i] * xd;
+    }
+    rec[tid] = ht;
+    rec[36 + tid] = hs;
+    rec[72 + tid] = hts;
+  } else if (tid >= 64 && tid < 70) {
+    const int i = tid - 64;
+    double bt = 0.0, bs = 0.0;
+    for (int a = 0; a < 6; a++) {
+      const double ca = sh.tot[21 + a];
+      bt += sh.X[a * 6 + i] * ca;
+      bs -= sh.D[a * 6 + i] * ca;
+    }
+    rec[108 + i] = bt;
+    rec[114 + i] = bs;
+  } else if (tid == 96) {
+    rec[120] = sh.tot[27];
+    rec[121] = sh.tot[28];
+#pragma unroll
+    for (int k = 122; k < B2_LINEARIZED_DOUBLES; k++) rec[k] = 0.0;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fused kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename PT, typename CT, int KIND, int MODE>
+__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM)
+factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
+  __shared__ Shared sh;
+  const int tid = threadIdx.x;
+  const uint32_t G = gridDim.x;
+
+  double acc[kAcc];
+  // pose at which residuals / Jacobians are evaluated (R, t) and rotation of the linearization point (Rl) for the fused covariance
+  double R[9], t[3], Rl_[9];
+  int cur = -1;
+
+  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += G) {
+    const int f = static_cast<int>(__ldg(tile_factor + tile));
+    if (f != cur) {
+      if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G);
+      __syncthreads();
+      if (tid < static_cast<int>(sizeof(FactorDesc) / 4)) {
+        reinterpret_cast<uint32_t*>(&sh.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + tid);
+      }
+      __syncthreads();
+      const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(sh.desc.out_index) * 16;
+      const double* pl = poses_lin + static_cast<size_t>(sh.desc.out_index) * 16;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          R[r * 3 + c] = __ldg(pe + r * 4 + c);
+          Rl_[r * 3 + c] = __ldg(pl + r * 4 + c);
+        }
+        t[r] = __ldg(pe + r * 4 + 3);
+      }
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
+      cur = f;
+    }
+
+    const FactorDesc& d = sh.desc;
+    const uint32_t n = d.n;
+    const size_t n_pad = d.n_pad;
+    const PT* __restrict__ px = static_cast<const PT*>(d.pts);
+    const CT* __restrict__ cv = static_cast<const CT*>(d.covs);
+    const uint32_t base = (tile - d.tile_begin) * kTile;
+
+#pragma unroll
+    for (int k = 0; k < kPointsPerThread; k++) {
+      const uint32_t i = base + k * kThreads + tid;
+      if (i >= n) continue;
+
+      const double x = ldv(px, i), y = ldv(px + n_pad, i), z = ldv(px + 2 * n_pad, i);
+      // u = R p, q = u + t : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU path)
+      const double u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
+      const double u1 = __dadd_rn(__dadd_rn(__dmul_rn(R[3], x), __dmul_rn(R[4], y)), __dmul_rn(R[5], z));
+      const double u2 = __dadd_rn(__dadd_rn(__dmul_rn(R[6], x), __dmul_rn(R[7], y)), __dmul_rn(R[8], z));
+      const double q0 = __dadd_rn(u0, t[0]), q1 = __dadd_rn(u1, t[1]), q2 = __dadd_rn(u2, t[2]);
+
+      // ---- correspondence ----
+      int id;
+      if (MODE == MODE_LINEARIZE) {
+        if (KIND == 0) {
+          id = lookup_voxel(d.buckets, d.bucket_mask, voxel_coord1(q0, d.inv_leaf), voxel_coord1(q1, d.inv_leaf), voxel_coord1(q2, d.inv_leaf));
+        } else {
+          const KdTreeView tv{d.nodes, d.leaf_pts, d.leaf_pts + d.leaf_n_pad, d.leaf_pts + 2 * static_cast<size_t>(d.leaf_n_pad)};
+          double sq;
+          id = kdtree_nn1(tv, q0, q1, q2, d.max_sq, &sq);
+        }
+        d.corr[i] = id;
+      } else {
+        id = __ldg(d.corr + i);  // frozen at the last linearize
+      }
+      if (id < 0) continue;
+
+      // ---- gather target record: mean(3) cov(6) ----
+      const double2* rec = reinterpret_cast<const double2*>(d.records + static_cast<size_t>(id) * kRecordDoubles);
+      const double2 r01 = __ldg(rec), r23 = __ldg(rec + 1), r45 = __ldg(rec + 2), r67 = __ldg(rec + 3), r89 = __ldg(rec + 4);
+      const double mb0 = r01.x, mb1 = r01.y, mb2 = r23.x;
+      const double b00 = r23.y, b01 = r45.x, b02 = r45.y, b11 = r67.x, b12 = r67.y, b22 = r89.x;
+
+      const double a00 = ldv(cv, i), a01 = ldv(cv + n_pad, i), a02 = ldv(cv + 2 * n_pad, i);
+      const double a11 = ldv(cv + 3 * n_pad, i), a12 = ldv(cv + 4 * n_pad, i), a22 = ldv(cv + 5 * n_pad, i);
+
+      // ---- fused covariance S = C_B + Rl C_A Rl^T (symmetric), M = S^-1 ----
+      double s00, s01, s02, s11, s12, s22;
+      {
+#define Rl(k) (MODE == MODE_ERROR ? Rl_[k] : R[k])
+        const double t00 = Rl(0) * a00 + Rl(1) * a01 + Rl(2) * a02;
+        const double t01 = Rl(0) * a01 + Rl(1) * a11 + Rl(2) * a12;
+        const double t02 = Rl(0) * a02 + Rl(1) * a12 + Rl(2) * a22;
+        s00 = b00 + (t00 * Rl(0) + t01 * Rl(1) + t02 * Rl(2));
+        s01 = b01 + (t00 * Rl(3) + t01 * Rl(4) + t02 * Rl(5));
+        s02 = b02 + (t00 * Rl(6) + t01 * Rl(7) + t02 * Rl(8));
+        const double t10 = Rl(3) * a00 + Rl(4) * a01 + Rl(5) * a02;
+        const double t11 = Rl(3) * a01 + Rl(4) * a11 + Rl(5) * a12;
+        const double t12 = Rl(3) * a02 + Rl(4) * a12 + Rl(5) * a22;
+        s11 = b11 + (t10 * Rl(3) + t11 * Rl(4) + t12 * Rl(5));
+        s12 = b12 + (t10 * Rl(6) + t11 * Rl(7) + t12 * Rl(8));
+        const double t20 = Rl(6) * a00 + Rl(7) * a01 + Rl(8) * a02;
+        const double t21 = Rl(6) * a01 + Rl(7) * a11 + Rl(8) * a12;
+        const double t22 = Rl(6) * a02 + Rl(7) * a12 + Rl(8) * a22;
+        s22 = b22 + (t20 * Rl(6) + t21 * Rl(7) + t22 * Rl(8));
+#undef Rl
+      }
+      const double c00 = s11 * s22 - s12 * s12;
+      const double c01 = s02 * s12 - s01 * s22;
+      const double c02 = s01 * s12 - s02 * s11;
+      const double c11 = s00 * s22 - s02 * s02;
+      const double c12 = s01 * s02 - s00 * s12;
+      const double c22 = s00 * s11 - s01 * s01;
+      const double inv_det = 1.0 / (s00 * c00 + s01 * c01 + s02 * c02);
+      const double m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
+      const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
+
+      // ---- residual, Mahalanobis error ----
+      const double e0 = mb0 - q0, e1 = mb1 - q1, e2 = mb2 - q2;
+      const double w0 = m00 * e0 + m01 * e1 + m02 * e2;
+      const double w1 = m01 * e0 + m11 * e1 + m12 * e2;
+      const double w2 = m02 * e0 + m12 * e1 + m22 * e2;
+      acc[27] += e0 * w0 + e1 * w1 + e2 * w2;
+      acc[28] += 1.0;
+
+      if (MODE == MODE_LINEARIZE) {
+        // K = hat(u) M  (column j = u x M[:,j])
+        const double k00 = u1 * m02 - u2 * m01, k10 = u2 * m00 - u0 * m02, k20 = u0 * m01 - u1 * m00;
+        const double k01 = u1 * m12 - u2 * m11, k11 = u2 * m01 - u0 * m12, k21 = u0 * m11 - u1 * m01;
+        const double k02 = u1 * m22 - u2 * m12, k12 = u2 * m02 - u0 * m22, k22 = u0 * m12 - u1 * m02;
+        // A_rr = K hat(u)^T
+        acc[0] += k02 * u1 - k01 * u2;
+        acc[1] += k00 * u2 - k02 * u0;
+        acc[2] += k01 * u0 - k00 * u1;
+        acc[3] += k10 * u2 - k12 * u0;
+        acc[4] += k11 * u0 - k10 * u1;
+        acc[5] += k21 * u0 - k20 * u1;
+        acc[6] += k00;
+        acc[7] += k01;
+        acc[8] += k02;
+        acc[9] += k10;
+        acc[10] += k11;
+        acc[11] += k12;
+        acc[12] += k20;
+        acc[13] += k21;
+        acc[14] += k22;
+        acc[15] += m00;
+        acc[16] += m01;
+        acc[17] += m02;
+        acc[18] += m11;
+        acc[19] += m12;
+        acc[20] += m22;
+        // c_r = u x (M r), c_t = M r
+        acc[21] += u1 * w2 - u2 * w1;
+        acc[22] += u2 * w0 - u0 * w2;
+        acc[23] += u0 * w1 - u1 * w0;
+        acc[24] += w0;
+        acc[25] += w1;
+        acc[26] += w2;
+      }
+    }
+  }
+  if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side: factor / factor-set objects
+// ---------------------------------------------------------------------------------------------------------------
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*);
+
+template <int KIND, int MODE>
+KernelFn pick_kernel(int pb, int cb) {
+  if (pb == 4 && cb == 4) return factor_kernel<float, float, KIND, MODE>;
+  if (pb == 4 && cb == 8) return factor_kernel<float, double, KIND, MODE>;
+  if (pb == 8 && cb == 4) return factor_kernel<double, float, KIND, MODE>;
+  return factor_kernel<double, double, KIND, MODE>;
+}
+
+KernelFn pick_kernel(int kind, int mode, int pb, int cb) {
+  if (kind == 0) return mode == MODE_LINEARIZE ? pick_kernel<0, MODE_LINEARIZE>(pb, cb) : pick_kernel<0, MODE_ERROR>(pb, cb);
+  return mode == MODE_LINEARIZE ? pick_kernel<1, MODE_LINEARIZE>(pb, cb) : pick_kernel<1, MODE_ERROR>(pb, cb);
+}
+
+struct Group {
+  int kind, pb, cb;
+  std::vector<size_t> members;  // indices into the set's factor list
+  FactorDesc* d_descs = nullptr;
+  uint32_t* d_tile_factor = nullptr;
+  uint32_t num_tiles = 0;
+  uint32_t grid[2] = {0, 0};
+  KernelFn fn[2] = {nullptr, nullptr};
+};
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_factor_set {
+  b2_ctx* ctx = nullptr;
+  std::vector<b2_factor*> factors;
+  std::vector<Group> groups;
+  double* d_partials = nullptr;
+  unsigned int* d_counters = nullptr;
+  double* d_poses_lin = nullptr;   // F x 16
+  double* d_poses_eval = nullptr;  // F x 16
+  double* d_out = nullptr;         // F x 128
+  double* d_err = nullptr;         // F
+  bool dev_lin_valid = false;      // d_poses_lin holds the linearization points of all factors
+  uint64_t launches = 0;
+};
+
+namespace {
+
+__global__ void scatter_corr_kernel(const int32_t* __restrict__ corr, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ leaf_index, size_t n,
+                                    long long* __restrict__ out) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int c = corr[i];
+  const long long v = c < 0 ? -1ll : (leaf_index ? static_cast<long long>(leaf_index[c]) : static_cast<long long>(c));
+  out[perm ? perm[i] : i] = v;
+}
+
+// GICP: target records (mean, cov, 1) in the tree's leaf order, gathered on the device from the target cloud's planes.
+template <typename PT, typename CT>
+__global__ void build_target_records_kernel(const PT* __restrict__ pts, const CT* __restrict__ covs, size_t n_pad, const uint32_t* __restrict__ cloud_inv_perm,
+                                            const uint32_t* __restrict__ leaf_index, size_t n, double* __restrict__ records) {
+  const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t caller = leaf_index[j];
+  const size_t s = cloud_inv_perm ? cloud_inv_perm[caller] : caller;
+  double* r = records + j * kRecordDoubles;
+  r[0] = static_cast<double>(pts[s]);
+  r[1] = static_cast<double>(pts[n_pad + s]);
+  r[2] = static_cast<double>(pts[2 * n_pad + s]);
+#pragma unroll
+  for (int k = 0; k < 6; k++) r[3 + k] = static_cast<double>(covs[k * n_pad + s]);
+  r[9] = 1.0;
+}
+
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ inv) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) inv[perm[i]] = static_cast<uint32_t>(i);
+}
+
+b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
+  cudaStream_t st = s->ctx->stream;
+  for (auto& g : s->groups) {
+    g.fn[mode]<<<g.grid[mode], kThreads, 0, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
+    s->launches++;
+  }
+  B2_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+b2_status b2_vgicp_factor_create(b2_ctx* ctx, const b2_voxelmap* target, const b2_cloud* source, b2_factor** out) {
+  B2_REQUIRE(out != nullptr, "b2_vgicp_factor_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_vgicp_factor_create: ctx is NULL");
+  // reference aborts on these (integrated_vgicp_factor_impl.hpp:32-45); the ABI reports them instead
+  B2_REQUIRE(source != nullptr && source->d_points != nullptr, "error: source points have not been allocated!!");
+  B2_REQUIRE(source->d_covs != nullptr, "error: source don't have covs!!");
+  B2_REQUIRE(target != nullptr, "error: target voxelmap has not been created!!");
+  B2_REQUIRE(target->ctx->device == ctx->device && source->ctx->device == ctx->device, "b2_vgicp_factor_create: handles live on different devices");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  b2_factor* f = new b2_factor;
+  f->ctx = ctx;
+  f->kind = B2_FACTOR_VGICP;
+  f->voxelmap = target;
+  f->source = source;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&f->d_corr), std::max<size_t>(source->n_pad, 1) * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    delete f;
+    return fail(B2_ERR_OUT_OF_MEMORY, "b2_vgicp_factor_create: %s", cudaGetErrorString(e));
+  }
+  *out = f;
+  return B2_OK;
+}
+
+b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const b2_kdtree* tree, const b2_cloud* source, b2_factor** out) {
+  B2_REQUIRE(out != nullptr, "b2_gicp_factor_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_gicp_factor_create: ctx is NULL");
+  // reference aborts on these (integrated_gicp_factor_impl.hpp:37-65)
+  B2_REQUIRE(source != nullptr && source->d_points != nullptr, "error: source points have not been allocated!!");
+  B2_REQUIRE(source->d_covs != nullptr, "error: source don't have covs!!");
+  B2_REQUIRE(target_cloud != nullptr && target_cloud->d_points != nullptr, "error: target points have not been allocated!!");
+  B2_REQUIRE(target_cloud->d_covs != nullptr, "error: target don't have covs!!");
+  B2_REQUIRE(tree != nullptr, "b2_gicp_factor_create: tree is NULL");
+  B2_REQUIRE(tree->n == target_cloud->n, "b2_gicp_factor_create: tree (%zu points) was not built over the target cloud (%zu points)", tree->n, target_cloud->n);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  b2_factor* f = new b2_factor;
+  f->ctx = ctx;
+  f->kind = B2_FACTOR_GICP;
+  f->target = target_cloud;
+  f->tree = tree;
+  f->source = source;
+  const size_t nt = tree->n;
+  cudaError_t e;
+  uint32_t* d_inv = nullptr;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&f->d_corr), std::max<size_t>(source->n_pad, 1) * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&f->d_target_records), std::max<size_t>(nt, 1) * kRecordDoubles * sizeof(double))) != cudaSuccess) {
+    b2_factor_destroy(f);
+    return fail(B2_ERR_OUT_OF_MEMORY, "b2_gicp_factor_create: %s", cudaGetErrorString(e));
+  }
+  if (nt > 0) {
+    const unsigned grid = static_cast<unsigned>((nt + 255) / 256);
+    if (target_cloud->d_perm) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&d_inv), nt * sizeof(uint32_t))) != cudaSuccess) {
+        b2_factor_destroy(f);
+        return fail(B2_ERR_OUT_OF_MEMORY, "b2_gicp_factor_create: %s", cudaGetErrorString(e));
+      }
+      invert_perm_kernel<<<grid, 256, 0, st>>>(target_cloud->d_perm, nt, d_inv);
+    }
+    const size_t np = target_cloud->n_pad;
+    if (target_cloud->point_bytes == 4 && target_cloud->cov_bytes == 4)
+      build_target_records_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(target_cloud->d_points), static_cast<const float*>(target_cloud->d_covs), np, d_inv, tree->d_leaf_index, nt, f->d_target_records);
+    else if (target_cloud->point_bytes == 4)
+      build_target_records_kernel<float, double><<<grid, 256, 0, st>>>(static_cast<const float*>(target_cloud->d_points), static_cast<const double*>(target_cloud->d_covs), np, d_inv, tree->d_leaf_index, nt, f->d_target_records);
+    else if (target_cloud->cov_bytes == 4)
+      build_target_records_kernel<double, float><<<grid, 256, 0, st>>>(static_cast<const double*>(target_cloud->d_points), static_cast<const float*>(target_cloud->d_covs), np, d_inv, tree->d_leaf_index, nt, f->d_target_records);
+    else
+      build_target_records_kernel<double, double><<<grid, 256, 0, st>>>(static_cast<const double*>(target_cloud->d_points), static_cast<const double*>(target_cloud->d_covs), np, d_inv, tree->d_leaf_index, nt, f->d_target_records);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_inv) cudaFree(d_inv);
+    if (e != cudaSuccess) {
+      b2_factor_destroy(f);
+      return fail(B2_ERR_CUDA, "b2_gicp_factor_create: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = f;
+  return B2_OK;
+}
+
+b2_status b2_factor_destroy(b2_factor* f) {
+  if (!f) return B2_OK;
+  cudaSetDevice(f->ctx->device);
+  if (f->self_set) b2_factor_set_destroy(f->self_set);
+  if (f->d_corr) cudaFree(f->d_corr);
+  if (f->d_target_records) cudaFree(f->d_target_records);
+  delete f;
+  return B2_OK;
+}
+
+b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist) {
+  B2_REQUIRE(f != nullptr, "b2_factor_set_max_correspondence_distance: factor is NULL");
+  B2_REQUIRE(dist >= 0.0, "b2_factor_set_max_correspondence_distance: negative distance");
+  f->max_corr_sq = dist * dist;  // integrated_gicp_factor.hpp:98-101
+  if (f->self_set) {             // descriptors embed max_sq: rebuild lazily
+    b2_factor_set_destroy(f->self_set);
+    f->self_set = nullptr;
+  }
+  return B2_OK;
+}
+
+size_t b2_factor_num_points(const b2_factor* f) { return f ? f->source->n : 0; }
+
+b2_status b2_factor_correspondences(const b2_factor* f, int64_t* out) {
+  B2_REQUIRE(f && out, "b2_factor_correspondences: NULL argument");
+  const size_t n = f->source->n;
+  if (n == 0) return B2_OK;
+  if (!f->linearized) {
+    for (size_t i = 0; i < n; i++) out[i] = -1;
+    return B2_OK;
+  }
+  B2_CUDA(cudaSetDevice(f->ctx->device));
+  cudaStream_t st = f->ctx->stream;
+  long long* d_out = nullptr;
+  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), n * sizeof(long long)));
+  scatter_corr_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f->d_corr, f->source->d_perm, f->kind == B2_FACTOR_GICP ? f->tree->d_leaf_index : nullptr, n, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(long long), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(B2_ERR_CUDA, "b2_factor_correspondences: %s", cudaGetErrorString(e));
+  return B2_OK;
+}
+
+// ---- factor sets ------------------------------------------------------------------------------------------------
+
+b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F, b2_factor_set** out) {
+  B2_REQUIRE(out != nullptr, "b2_factor_set_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_factor_set_create: ctx is NULL");
+  B2_REQUIRE(F > 0 && factors != nullptr, "b2_factor_set_create: empty factor list");
+  for (size_t i = 0; i < F; i++) {
+    B2_REQUIRE(factors[i] != nullptr, "b2_factor_set_create: factor %zu is NULL", i);
+    B2_REQUIRE(factors[i]->ctx->device == ctx->device, "b2_factor_set_create: factor %zu lives on another device", i);
+  }
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+
+  b2_factor_set* s = new b2_factor_set;
+  s->ctx = ctx;
+  s->factors.assign(factors, factors + F);
+
+  std::map<std::tuple<int, int, int>, size_t> group_of;
+  for (size_t i = 0; i < F; i++) {
+    const b2_factor* f = factors[i];
+    const auto key = std::make_tuple(static_cast<int>(f->kind), f->source->point_bytes, f->source->cov_bytes);
+    auto it = group_of.find(key);
+    if (it == group_of.end()) {
+      it = group_of.emplace(key, s->groups.size()).first;
+      Group g;
+      g.kind = f->kind;
+      g.pb = f->source->point_bytes;
+      g.cb = f->source->cov_bytes;
+      s->groups.push_back(g);
+    }
+    s->groups[it->second].members.push_back(i);
+  }
+
+  auto fail_cleanup = [&](b2_status stt) {
+    b2_factor_set_destroy(s);
+    return stt;
+  };
+
+  uint32_t slot_cursor = 0;
+  for (auto& g : s->groups) {
+    std::vector<FactorDesc> descs(g.members.size());
+    std::vector<uint32_t> tile_factor;
+    uint32_t tile_cursor = 0;
+    for (size_t k = 0; k < g.members.size(); k++) {
+      const b2_factor* f = factors[g.members[k]];
+      FactorDesc& d = descs[k];
+      std::memset(&d, 0, sizeof(d));
+      d.pts = f->source->d_points;
+      d.covs = f->source->d_covs;
+      d.n = static_cast<uint32_t>(f->source->n);
+      d.n_pad = static_cast<uint32_t>(f->source->n_pad);
+      if (f->kind == B2_FACTOR_VGICP) {
+        d.buckets = f->voxelmap->d_buckets;
+        d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets - 1);
+        d.inv_leaf = f->voxelmap->inv_resolution;
+        d.records = f->voxelmap->d_records;
+      } else {
+        d.nodes = f->tree->d_nodes;
+        d.leaf_pts = f->tree->d_leaf_points;
+        d.leaf_n_pad = static_cast<uint32_t>(f->tree->n_pad);
+        d.max_sq = f->max_corr_sq;
+        d.records = f->d_target_records;
+      }
+      d.corr = f->d_corr;
+      d.tile_begin = tile_cursor;
+      d.num_tiles = std::max<uint32_t>(1u, (d.n + kTile - 1) / kTile);
+      d.out_index = static_cast<uint32_t>(g.members[k]);
+      tile_cursor += d.num_tiles;
+      tile_factor.insert(tile_factor.end(), d.num_tiles, static_cast<uint32_t>(k));
+    }
+    g.num_tiles = tile_cursor;
+    for (int mode = 0; mode < 2; mode++) {
+      g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb);
+      int per_sm = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], kThreads, 0);
+      if (e != cudaSuccess || per_sm < 1) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: occupancy query failed (%s)", cudaGetErrorString(e)));
+      g.grid[mode] = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count * per_sm));
+      for (auto& d : descs) {
+        d.num_slots[mode] = std::min<uint32_t>(d.num_tiles, g.grid[mode]);
+        d.slot_begin[mode] = slot_cursor;
+        slot_cursor += d.num_slots[mode];
+      }
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&g.d_descs), descs.size() * sizeof(FactorDesc))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&g.d_tile_factor), tile_factor.size() * sizeof(uint32_t))) != cudaSuccess) {
+      return fail_cleanup(fail(B2_ERR_OUT_OF_MEMORY, "b2_factor_set_create: %s", cudaGetErrorString(e)));
+    }
+    if ((e = cudaMemcpyAsync(g.d_descs, descs.data(), descs.size() * sizeof(FactorDesc), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(g.d_tile_factor, tile_factor.data(), tile_factor.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+      return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: %s", cudaGetErrorString(e)));
+    }
+  }
+
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_partials), static_cast<size_t>(slot_cursor) * kAcc * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_counters), F * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_poses_lin), F * 16 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_poses_eval), F * 16 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_out), F * B2_LINEARIZED_DOUBLES * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_err), F * sizeof(double))) != cudaSuccess) {
+    return fail_cleanup(fail(B2_ERR_OUT_OF_MEMORY, "b2_factor_set_create: %s", cudaGetErrorString(e)));
+  }
+  if ((e = cudaMemsetAsync(s->d_counters, 0, F * sizeof(unsigned int), st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+    return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: %s", cudaGetErrorString(e)));
+  }
+  b2_status ss = ctx->ensure_stage(F * (B2_LINEARIZED_DOUBLES + 32) * sizeof(double), 0);
+  if (ss != B2_OK) return fail_cleanup(ss);
+  *out = s;
+  return B2_OK;
+}
+
+b2_status b2_factor_set_destroy(b2_factor_set* s) {
+  if (!s) return B2_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (auto& g : s->groups) {
+    if (g.d_descs) cudaFree(g.d_descs);
+    if (g.d_tile_factor) cudaFree(g.d_tile_factor);
+  }
+  if (s->d_partials) cudaFree(s->d_partials);
+  if (s->d_counters) cudaFree(s->d_counters);
+  if (s->d_poses_lin) cudaFree(s->d_poses_lin);
+  if (s->d_poses_eval) cudaFree(s->d_poses_eval);
+  if (s->d_out) cudaFree(s->d_out);
+  if (s->d_err) cudaFree(s->d_err);
+  delete s;
+  return B2_OK;
+}
+
+size_t b2_factor_set_size(const b2_factor_set* s) { return s ? s->factors.size() : 0; }
+uint64_t b2_factor_set_launch_count(const b2_factor_set* s) { return s ? s->launches : 0; }
+
+b2_status b2_factor_set_linearize_device(b2_factor_set* s, const double* d_deltas, double* d_out) {
+  B2_REQUIRE(s && d_deltas && d_out, "b2_factor_set_linearize_device: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  const size_t F = s->factors.size();
+  if (d_deltas != s->d_poses_lin) B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, d_deltas, F * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s->ctx->stream));
+  B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out));
+  s->dev_lin_valid = true;
+  for (auto* f : s->factors) f->linearized = true;
+  return B2_OK;
+}
+
+b2_status b2_factor_set_error_device(b2_factor_set* s, const double* d_deltas_eval, double* d_out_errors) {
+  B2_REQUIRE(s && d_deltas_eval && d_out_errors, "b2_factor_set_error_device: NULL argument");
+  if (!s->dev_lin_valid) return fail(B2_ERR_INVALID_STATE, "b2_factor_set_error_device: the set has not been linearized yet");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, d_deltas_eval, d_out_errors));
+  return B2_OK;
+}
+
+b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_linearized* out) {
+  B2_REQUIRE(s && deltas && out, "b2_factor_set_linearize: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  cudaStream_t st = s->ctx->stream;
+  const size_t F = s->factors.size();
+  const size_t in_bytes = F * 16 * sizeof(double), out_bytes = F * sizeof(b2_linearized);
+  B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
+  char* h = static_cast<char*>(s->ctx->h_stage);
+  std::memcpy(h, deltas, in_bytes);
+  B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
+  B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out));
+  B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(out, h + in_bytes, out_bytes);
+  s->dev_lin_valid = true;
+  for (size_t i = 0; i < F; i++) {
+    s->factors[i]->linearized = true;
+    std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
+  }
+  return B2_OK;
+}
+
+b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, double* out_errors) {
+  B2_REQUIRE(s && deltas_eval && out_errors, "b2_factor_set_error: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  cudaStream_t st = s->ctx->stream;
+  const size_t F = s->factors.size();
+  if (!s->dev_lin_valid) {
+    // First evaluation before any linearization: the reference establishes the correspondences at the evaluation
+    // point (integrated_vgicp_factor_impl.hpp:183-185) -- i.e. a linearize at delta_eval whose error is returned.
+    std::vector<b2_linearized> lin(F);
+    B2_TRY(b2_factor_set_linearize(s, deltas_eval, lin.data()));
+    for (size_t i = 0; i < F; i++) out_errors[i] = lin[i].error;
+    return B2_OK;
+  }
+  const size_t in_bytes = F * 16 * sizeof(double), out_bytes = F * sizeof(double);
+  B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
+  char* h = static_cast<char*>(s->ctx->h_stage);
+  std::memcpy(h, deltas_eval, in_bytes);
+  B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));
+  B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, s->d_poses_eval, s->d_err));
+  B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_err, out_bytes, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(out_errors, h + in_bytes, out_bytes);
+  return B2_OK;
+}
+
+// ---- single-factor conveniences ---------------------------------------------------------------------------------
+
+static b2_status ensure_self_set(b2_factor* f) {
+  if (f->self_set) return B2_OK;
+  b2_factor* one[1] = {f};
+  return b2_factor_set_create(f->ctx, one, 1, &f->self_set);
+}
+
+b2_status b2_factor_linearize(b2_factor* f, const double* delta, b2_linearized* out) {
+  B2_REQUIRE(f && delta && out, "b2_factor_linearize: NULL argument");
+  B2_TRY(ensure_self_set(f));
+  return b2_factor_set_linearize(f->self_set, delta, out);
+}
+
+b2_status b2_factor_error(b2_factor* f, const double* delta_eval, double* out_error) {
+  B2_REQUIRE(f && delta_eval && out_error, "b2_factor_error: NULL argument");
+  B2_TRY(ensure_self_set(f));
+  return b2_factor_set_error(f->self_set, delta_eval, out_error);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""Host-side mirrors of the reference's data types for the scan-matching path.
+
+Names and argument meaning follow the reference (paths relative to its root):
+  PointCloud            include/gtsam_points/types/point_cloud.hpp:19-119 (+ PointCloudCPU / PointCloudGPU)
+  GaussianVoxelMapGPU   include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:39-108
+  KdTree                include/gtsam_points/ann/kdtree.hpp, ann/nearest_neighbor_search.hpp:16-57
+All device work goes through the C ABI (include/b2points.h); nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import capi
+
+_ctx_lock = threading.Lock()
+_default_ctx = {}
+
+
+class Context:
+    """Device + stream (b2_ctx).  `stream` is an integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        capi.check(capi.lib().b2_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def synchronize(self):
+        capi.check(capi.lib().b2_ctx_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return capi.lib().b2_ctx_stream(self.h) or 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().b2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_context(device: int = 0) -> Context:
+    with _ctx_lock:
+        if device not in _default_ctx:
+            _default_ctx[device] = Context(device)
+        return _default_ctx[device]
+
+
+class PointCloud:
+    """Points (N x 3 or N x 4 float64) with optional covariances (N x 3 x 3 or N x 4 x 4 float64).
+
+    The device copy (`points_gpu` / `covs_gpu` in the reference) is created on construction.
+    flags: capi.B2_CLOUD_* (default lossless storage, Morton-ordered on the device).
+    """
+
+    def __init__(self, points, covs=None, ctx: Context | None = None, flags: int = capi.B2_CLOUD_DEFAULT):
+        self.ctx = ctx or default_context()
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        if self.points.ndim != 2 or self.points.shape[1] not in (3, 4):
+            raise ValueError("points must be N x 3 or N x 4")
+        self.covs = None
+        cov_stride = 0
+        if covs is not None:
+            covs = np.ascontiguousarray(covs, dtype=np.float64)
+            if covs.shape[1:] == (3, 3):
+                cov_stride = 9
+            elif covs.shape[1:] == (4, 4):
+                cov_stride = 16
+            else:
+                raise ValueError("covs must be N x 3 x 3 or N x 4 x 4")
+            if len(covs) != len(self.points):
+                raise ValueError("points / covs size mismatch")
+            self.covs = covs
+        h = C.c_void_p()
+        capi.check(
+            capi.lib().b2_cloud_create(
+                self.ctx.h, capi.dptr(self.points), self.points.shape[1], capi.dptr(self.covs) if self.covs is not None else None, cov_stride, len(self.points), flags, C.byref(h)
+            )
+        )
+        self.h = h
+
+    def size(self) -> int:
+        return len(self.points)
+
+    def __len__(self):
+        return len(self.points)
+
+    def has_points(self):
+        return True
+
+    def has_covs(self):
+        return self.covs is not None
+
+    def info(self) -> capi.CloudInfo:
+        info = capi.CloudInfo()
+        capi.check(capi.lib().b2_cloud_get_info(self.h, C.byref(info)))
+        return info
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                capi.lib().b2_cloud_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class GaussianVoxelMapGPU:
+    """Gaussian voxel map on the device with the CPU map's index semantics (first-touch ids, exact lookups)."""
+
+    def __init__(self, resolution: float, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self._resolution = float(resolution)
+        self.h = None
+
+    def voxel_resolution(self) -> float:
+        return self._resolution
+
+    def insert(self, frame: PointCloud):
+        """One-shot build (the reference's GPU map does not support incremental insertion either:
+        include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:63)."""
+        if self.h is not None:
+            raise RuntimeError("GaussianVoxelMapGPU.insert: incremental insertion is not supported on the GPU")
+        if frame.covs is None:
+            raise ValueError("GaussianVoxelMapGPU.insert: the frame has no covariances")
+        h = C.c_void_p()
+        cov_stride = 9 if frame.covs.shape[1:] == (3, 3) else 16
+        capi.check(
+            capi.lib().b2_voxelmap_create_from_points(self.ctx.h, self._resolution, capi.dptr(frame.points), frame.points.shape[1], capi.dptr(frame.covs), cov_stride, len(frame.points), C.byref(h))
+        )
+        self.h = h
+
+    @classmethod
+    def from_voxels(cls, resolution, coords, means, covs, num_points=None, ctx: Context | None = None):
+        """Upload an existing map (e.g. the contents of a GaussianVoxelMapCPU); ids = the given order."""
+        self = cls(resolution, ctx)
+        coords = np.ascontiguousarray(coords, dtype=np.int32)
+        means = np.ascontiguousarray(means, dtype=np.float64)
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(len(coords), 9)
+        npts = None if num_points is None else np.ascontiguousarray(num_points, dtype=np.int32)
+        h = C.c_void_p()
+        capi.check(
+            capi.lib().b2_voxelmap_create_from_voxels(
+                self.ctx.h, float(resolution), coords.ctypes.data_as(C.POINTER(C.c_int32)), capi.dptr(means), capi.dptr(covs), None if npts is None else npts.ctypes.data_as(C.POINTER(C.c_int32)), len(coords), C.byref(h)
+            )
+        )
+        self.h = h
+        return self
+
+    def info(self) -> capi.VoxelMapInfo:
+        info = capi.VoxelMapInfo()
+        capi.check(capi.lib().b2_voxelmap_get_info(self.h, C.byref(info)))
+        return info
+
+    @property
+    def num_voxels(self) -> int:
+        return int(self.info().num_voxels)
+
+    def download(self):
+        """download_voxel_means / _covs / _num_points + voxel coordinates, in id order."""
+        V = self.num_voxels
+        coords = np.zeros((V, 3), dtype=np.int32)
+        means = np.zeros((V, 3))
+        covs = np.zeros((V, 3, 3))
+        n = np.zeros(V, dtype=np.int32)
+        capi.check(capi.lib().b2_voxelmap_download(self.h, coords.ctypes.data_as(C.POINTER(C.c_int32)), capi.dptr(means), capi.dptr(covs), n.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(coords=coords, means=means, covs=covs, n=n, resolution=self._resolution)
+
+    def lookup_voxel_index(self, points) -> np.ndarray:
+        """voxel_coord + lookup_voxel_index for a batch of points; -1 where no voxel exists."""
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        out = np.zeros(len(p), dtype=np.int32)
+        capi.check(capi.lib().b2_voxelmap_lookup(self.h, capi.dptr(p), p.shape[1], len(p), out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                capi.lib().b2_voxelmap_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class KdTree:
+    """NearestNeighborSearch over a point set, exact 1-NN on the device."""
+
+    def __init__(self, points, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.points = np.ascontiguousarray(points.points if isinstance(points, PointCloud) else points, dtype=np.float64)
+        h = C.c_void_p()
+        capi.check(capi.lib().b2_kdtree_create(self.ctx.h, capi.dptr(self.points), self.points.shape[1], len(self.points), C.byref(h)))
+        self.h = h
+
+    def knn_search(self, queries, k: int = 1, max_sq_dist: float = np.finfo(np.float64).max):
+        """Batched knn_search(pt, 1, ...): returns (indices int64 [-1 = none], squared distances)."""
+        if k != 1:
+            raise NotImplementedError("the device kd-tree answers k = 1 (the GICP correspondence search)")
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        if q.ndim == 1:
+            q = q[None]
+        idx = np.zeros(len(q), dtype=np.int64)
+        sqd = np.zeros(len(q))
+        capi.check(capi.lib().b2_kdtree_knn1(self.h, capi.dptr(q), q.shape[1], len(q), float(max_sq_dist), idx.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(sqd)))
+        return idx, sqd
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                capi.lib().b2_kdtree_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

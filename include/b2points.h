@@ -1,0 +1,202 @@
+/*
+ * b2points.h -- C ABI of the B200-native scan-matching linearization library (libb2points.so).
+ *
+ * This is the drop-in boundary for the per-point correspondence + linearization hot path of
+ * koide3/gtsam_points.  Plain C: opaque handles, raw pointers, sizes.  No C++
+ * types, no torch types, no exceptions; every function returns a b2_status and leaves a message
+ * retrievable with b2_last_error() on failure.  The library never frees or retains caller memory:
+ * host inputs are copied (to the device) before a call returns.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ * The GTSAM-typed adapter classes that keep the reference's C++ surface on top of this ABI live in
+ * gtsam_points_b200/cpp/ ; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - poses / deltas: 4x4 row-major double, delta = T_target^-1 * T_source
+ *     (src/gtsam_points/factors/integrated_matching_cost_factor.cpp:57-69).
+ *   - points: `point_stride` doubles per point (3 = packed xyz, 4 = the reference's Vector4d (x,y,z,1),
+ *     include/gtsam_points/types/point_cloud.hpp:106).
+ *   - covariances: `cov_stride` doubles per point (9 = 3x3, 16 = the reference's Matrix4d with zero
+ *     row/col 3, point_cloud.hpp:108); symmetric, so row- and column-major coincide.
+ *   - tangent ordering of H, b: GTSAM Pose3 [rotation(3), translation(3)].
+ *   - all 6x6 blocks are row-major; H_target_source = sum J_target^T M J_source.
+ *   - b_* are the raw sums J^T M r; the HessianFactor takes -b
+ *     (integrated_matching_cost_factor.cpp:46-52).
+ */
+#ifndef B2POINTS_H_
+#define B2POINTS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2_API
+#else
+#define B2_API __attribute__((visibility("default")))
+#endif
+
+typedef enum b2_status {
+  B2_OK = 0,
+  B2_ERR_INVALID_ARGUMENT = 1,
+  B2_ERR_CUDA = 2,
+  B2_ERR_OUT_OF_MEMORY = 3,
+  B2_ERR_INVALID_STATE = 4,
+  B2_ERR_NO_DEVICE = 5
+} b2_status;
+
+typedef struct b2_ctx b2_ctx;               /* device + stream + staging buffers                                  */
+typedef struct b2_cloud b2_cloud;           /* device copy of a PointCloud (points + covs)                        */
+typedef struct b2_voxelmap b2_voxelmap;     /* GaussianVoxelMapGPU replacement                                    */
+typedef struct b2_kdtree b2_kdtree;         /* NearestNeighborSearch / KdTree replacement on the device           */
+typedef struct b2_factor b2_factor;         /* Integrated{VGICP,GICP}Factor device state                          */
+typedef struct b2_factor_set b2_factor_set; /* NonlinearFactorSetGPU replacement: one batched launch over factors */
+
+/* One linearized factor.  Replaces `LinearizedSystem6` (include/gtsam_points/cuda/kernels/linearized_system.cuh:10-71)
+ * and the five out-parameters of IntegratedMatchingCostFactor::evaluate
+ * (include/gtsam_points/factors/integrated_matching_cost_factor.hpp:74-83).  128 doubles = 1 KiB. */
+typedef struct b2_linearized {
+  double H_target[36];
+  double H_source[36];
+  double H_target_source[36];
+  double b_target[6];
+  double b_source[6];
+  double error;       /* sum r^T M r (not halved)                      */
+  double num_inliers; /* number of source points with a correspondence */
+  double reserved[6];
+} b2_linearized;
+
+#define B2_LINEARIZED_DOUBLES 128
+
+/* b2_cloud_create flags */
+#define B2_CLOUD_DEFAULT 0u
+#define B2_CLOUD_NO_REORDER 1u   /* keep the caller's point order on the device (default: Morton order)                       */
+#define B2_CLOUD_COMPACT_F32 2u  /* store points AND covariances as float32 even if that rounds them: the reference's        \
+                                    PointCloudGPU layout (point_cloud.hpp:115-117).  Default is lossless: float32 storage is \
+                                    chosen per array only when every value is exactly float32-representable, else float64.   */
+#define B2_CLOUD_FORCE_F64 4u    /* always store float64                                                                     */
+
+typedef struct b2_cloud_info {
+  uint64_t num_points;
+  int32_t point_bytes;     /* 4 or 8: storage type of coordinates */
+  int32_t cov_bytes;       /* 4 or 8: storage type of covariances, 0 = no covariances */
+  int32_t reordered;       /* 1 if stored in Morton order */
+  int32_t reserved;
+  uint64_t device_bytes;
+} b2_cloud_info;
+
+typedef struct b2_voxelmap_info {
+  uint64_t num_voxels;
+  uint64_t num_buckets;
+  double resolution;
+  uint64_t device_bytes;
+} b2_voxelmap_info;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Library / context
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Message of the last failing call on this thread ("" if none). */
+B2_API const char* b2_last_error(void);
+B2_API const char* b2_version(void);
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t the caller owns (e.g. torch's current
+ * stream) or NULL to let the context create its own non-blocking stream.  Replaces the reference's per-object
+ * CUstream_st* arguments and StreamTempBufferRoundRobin (include/gtsam_points/cuda/stream_temp_buffer_roundrobin.hpp:49-65). */
+B2_API b2_status b2_ctx_create(int device, void* stream, b2_ctx** out);
+B2_API b2_status b2_ctx_destroy(b2_ctx* ctx);
+B2_API b2_status b2_ctx_synchronize(b2_ctx* ctx);
+B2_API void* b2_ctx_stream(b2_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Point clouds.  Replaces PointCloudGPU's upload of points/covs (src/gtsam_points/types/point_cloud_gpu.cu)
+ * as consumed through frame::traits (include/gtsam_points/types/frame_traits.hpp:27-168).
+ * ---------------------------------------------------------------------------------------------------------- */
+B2_API b2_status b2_cloud_create(b2_ctx* ctx, const double* points, int point_stride, const double* covs, int cov_stride, size_t n,
+                                 unsigned flags, b2_cloud** out);
+B2_API b2_status b2_cloud_destroy(b2_cloud* cloud);
+B2_API b2_status b2_cloud_get_info(const b2_cloud* cloud, b2_cloud_info* info);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Gaussian voxel map.  Replaces GaussianVoxelMapGPU (include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:39-108)
+ * with the index semantics of GaussianVoxelMapCPU (src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:59-77):
+ * voxel ids are first-touch order, no point is ever dropped, lookups are exact.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One-shot build on the device from a host cloud: GaussianVoxelMap::insert(const PointCloud&)
+ * (include/gtsam_points/types/gaussian_voxelmap.hpp:27; CPU semantics ann/impl/incremental_voxelmap_impl.hpp:31-68). */
+B2_API b2_status b2_voxelmap_create_from_points(b2_ctx* ctx, double resolution, const double* points, int point_stride, const double* covs,
+                                                int cov_stride, size_t n, b2_voxelmap** out);
+/* Upload an existing map (e.g. a GaussianVoxelMapCPU's flat_voxels or a save_compact file,
+ * include/gtsam_points/types/gaussian_voxel_data.hpp:11-54): coords V x 3, means V x 3, covs V x 9, num_points V. */
+B2_API b2_status b2_voxelmap_create_from_voxels(b2_ctx* ctx, double resolution, const int32_t* coords, const double* means, const double* covs,
+                                                const int32_t* num_points, size_t num_voxels, b2_voxelmap** out);
+B2_API b2_status b2_voxelmap_destroy(b2_voxelmap* vm);
+B2_API b2_status b2_voxelmap_get_info(const b2_voxelmap* vm, b2_voxelmap_info* info);
+/* download_voxel_means / _covs / _num_points / buckets (gaussian_voxelmap_gpu.hpp:110-114); any pointer may be NULL */
+B2_API b2_status b2_voxelmap_download(const b2_voxelmap* vm, int32_t* coords, double* means, double* covs, int32_t* num_points);
+/* voxel_coord + lookup_voxel_index for n host points (gaussian_voxelmap_cpu.cpp:59-69); out_index[i] = id or -1 */
+B2_API b2_status b2_voxelmap_lookup(const b2_voxelmap* vm, const double* points, int point_stride, size_t n, int32_t* out_index);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Nearest-neighbour search.  Replaces NearestNeighborSearch::knn_search for k = 1
+ * (include/gtsam_points/ann/nearest_neighbor_search.hpp:31-35, ann/kdtree2.hpp:52-61): exact.
+ * ---------------------------------------------------------------------------------------------------------- */
+B2_API b2_status b2_kdtree_create(b2_ctx* ctx, const double* points, int point_stride, size_t n, b2_kdtree** out);
+B2_API b2_status b2_kdtree_destroy(b2_kdtree* tree);
+/* queries: host, nq x query_stride doubles.  out_index[i] = index of the nearest target point with squared distance
+ * < max_sq_dist, else -1; out_sq_dist[i] = its squared distance (max_sq_dist if none).  Either output may be NULL. */
+B2_API b2_status b2_kdtree_knn1(const b2_kdtree* tree, const double* queries, int query_stride, size_t nq, double max_sq_dist, int64_t* out_index,
+                                double* out_sq_dist);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Factors.  Replace IntegratedVGICPFactor_ / IntegratedVGICPFactorGPU and IntegratedGICPFactor_
+ * (include/gtsam_points/factors/integrated_vgicp_factor.hpp:37-54, integrated_vgicp_factor_gpu.hpp:43-66,
+ *  integrated_gicp_factor.hpp:44-78).  A factor retains its target / source handles (they must outlive it).
+ * ---------------------------------------------------------------------------------------------------------- */
+B2_API b2_status b2_vgicp_factor_create(b2_ctx* ctx, const b2_voxelmap* target, const b2_cloud* source, b2_factor** out);
+/* target_cloud must carry covariances; tree must have been built over the same target points. */
+B2_API b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const b2_kdtree* tree, const b2_cloud* source, b2_factor** out);
+B2_API b2_status b2_factor_destroy(b2_factor* f);
+/* IntegratedGICPFactor_::set_max_correspondence_distance (integrated_gicp_factor.hpp:98-101); default 1.0 */
+B2_API b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist);
+B2_API size_t b2_factor_num_points(const b2_factor* f);
+/* Correspondences frozen at the last linearize, in the caller's point order: VGICP voxel id / GICP target index, -1 = none
+ * (IntegratedVGICPFactor_::correspondences, integrated_vgicp_factor.hpp:107; IntegratedGICPFactor_::correspondences :147). */
+B2_API b2_status b2_factor_correspondences(const b2_factor* f, int64_t* out);
+
+/* linearize(): update_correspondences(delta) + evaluate(delta, H..., b...) in one fused pass
+ * (integrated_matching_cost_factor.cpp:37-55).  Single-factor convenience wrappers around a factor set of size 1. */
+B2_API b2_status b2_factor_linearize(b2_factor* f, const double* delta, b2_linearized* out);
+/* error(): evaluate(delta_eval) re-using the correspondences and fused covariances frozen at the last linearize
+ * (integrated_matching_cost_factor.cpp:32-35, integrated_vgicp_factor_impl.hpp:183-224).  If the factor has never been
+ * linearized, correspondences are first established at delta_eval (integrated_vgicp_factor_impl.hpp:183-185). */
+B2_API b2_status b2_factor_error(b2_factor* f, const double* delta_eval, double* out_error);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Factor sets.  Replace NonlinearFactorSetGPU::linearize / ::error
+ * (src/gtsam_points/cuda/nonlinear_factor_set_gpu.cpp:64-139, :141-218): all factors of the set are evaluated by
+ * ONE kernel launch per (factor kind, storage type) group, one H2D of the poses and one D2H of the results.
+ * ---------------------------------------------------------------------------------------------------------- */
+B2_API b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t num_factors, b2_factor_set** out);
+B2_API b2_status b2_factor_set_destroy(b2_factor_set* set);
+B2_API size_t b2_factor_set_size(const b2_factor_set* set);
+/* deltas: host, F x 16 doubles; out: host, F records.  Blocks until the results are on the host. */
+B2_API b2_status b2_factor_set_linearize(b2_factor_set* set, const double* deltas, b2_linearized* out);
+/* deltas_eval: host, F x 16; out_errors: host, F doubles. */
+B2_API b2_status b2_factor_set_error(b2_factor_set* set, const double* deltas_eval, double* out_errors);
+/* Device-resident variants for callers that keep poses / results on the GPU (multi-GPU all-reduce of the result
+ * buffer, kernel-only timing): d_deltas F x 16 doubles, d_out F x 128 doubles, both device pointers valid on the
+ * context's stream.  Asynchronous: no host synchronisation; ordering is the stream's. */
+B2_API b2_status b2_factor_set_linearize_device(b2_factor_set* set, const double* d_deltas, double* d_out);
+B2_API b2_status b2_factor_set_error_device(b2_factor_set* set, const double* d_deltas_eval, double* d_out_errors);
+/* Number of kernel launches issued by this set since creation (for bench.py's gpu_launches). */
+B2_API uint64_t b2_factor_set_launch_count(const b2_factor_set* set);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2POINTS_H_ */
