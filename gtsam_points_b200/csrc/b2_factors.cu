@@ -111,7 +111,8 @@ struct Shared {
 
 template <int MODE>
 __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], const double (&Rr)[9], const double (&tr)[3], double* __restrict__ partials,
-                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G) {
+                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G, const double* __restrict__ poses_lin,
+                                             double* __restrict__ lin_store) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double w = warp_reduce32(v, lane);
   sh.red[warp][lane] = w;
@@ -225,6 +226,9 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
     }
     rec[108 + i] = bt;
     rec[114 + i] = bs;
+  } else if (tid >= 128 && tid < 144) {
+    // remember the linearization point on the device (error-only launches read it back); a different buffer than poses_lin
+    if (lin_store) lin_store[static_cast<size_t>(d.out_index) * 16 + (tid - 128)] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (tid - 128));
   } else if (tid == 96) {
     rec[120] = sh.tot[27];
     rec[121] = sh.tot[28];
@@ -240,7 +244,8 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
 template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
-              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
+              double* __restrict__ lin_store) {
   __shared__ Shared sh;
   const int tid = threadIdx.x;
   const uint32_t G = gridDim.x;
@@ -253,7 +258,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
   for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += G) {
     const int f = static_cast<int>(__ldg(tile_factor + tile));
     if (f != cur) {
-      if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G);
+      if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
       __syncthreads();
       if (tid < static_cast<int>(sizeof(FactorDesc) / 4)) {
         reinterpret_cast<uint32_t*>(&sh.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + tid);
@@ -395,13 +400,13 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       }
     }
   }
-  if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G);
+  if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
 // ---------------------------------------------------------------------------------------------------------------
-using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*);
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, double*);
 
 template <int KIND, int MODE>
 KernelFn pick_kernel(int pb, int cb) {
@@ -479,8 +484,9 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, 
 
 b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
   cudaStream_t st = s->ctx->stream;
+  double* lin_store = (mode == MODE_LINEARIZE && d_lin != s->d_poses_lin) ? s->d_poses_lin : nullptr;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kThreads, 0, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
+    g.fn[mode]<<<g.grid[mode], kThreads, 0, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, lin_store);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -755,8 +761,9 @@ b2_status b2_factor_set_linearize_device(b2_factor_set* s, const double* d_delta
   B2_REQUIRE(s && d_deltas && d_out, "b2_factor_set_linearize_device: NULL argument");
   B2_CUDA(cudaSetDevice(s->ctx->device));
   const size_t F = s->factors.size();
-  if (d_deltas != s->d_poses_lin) B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, d_deltas, F * 16 * sizeof(double), cudaMemcpyDeviceToDevice, s->ctx->stream));
-  B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out));
+  (void)F;
+  // one launch per group, nothing else: the kernel's per-factor epilogue also stores the linearization point on the device
+  B2_TRY(launch_groups(s, MODE_LINEARIZE, d_deltas, d_deltas, d_out));
   s->dev_lin_valid = true;
   for (auto* f : s->factors) f->linearized = true;
   return B2_OK;

@@ -169,8 +169,9 @@ struct XORVec3iHash {
 struct orc_cloud {
   std::vector<Vec4> points;
   std::vector<Mat4> covs;
+  bool covs_given = false;
   size_t size() const { return points.size(); }
-  bool has_covs() const { return !covs.empty(); }
+  bool has_covs() const { return covs_given; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -714,6 +715,7 @@ orc_cloud* orc_cloud_create(const double* xyz, const double* cov3x3, size_t n) {
   c->points.resize(n);
   for (size_t i = 0; i < n; i++) c->points[i] = Vec4{{xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2], 1.0}};
   if (cov3x3) {
+    c->covs_given = true;
     c->covs.resize(n);
     for (size_t i = 0; i < n; i++) {
       c->covs[i].set_zero();

@@ -86,7 +86,8 @@ class Cloud:
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.covs = None if covs is None else np.ascontiguousarray(covs, dtype=np.float64).reshape(len(pts), 9)
         self.n = len(self.pts)
-        self.h = lib().orc_cloud_create(_dp(self.pts), None if self.covs is None else _dp(self.covs), self.n)
+        dummy = np.zeros(1)  # keep the pointers non-NULL for empty clouds
+        self.h = lib().orc_cloud_create(_dp(self.pts) if self.n else _dp(dummy), None if self.covs is None else (_dp(self.covs) if self.n else _dp(dummy)), self.n)
 
     def __del__(self):
         if getattr(self, "h", None):
