@@ -32,10 +32,10 @@
 namespace b2 {
 
 constexpr int kThreads = 256;
-constexpr int kPointsPerThread = 2;
+constexpr int kPointsPerThread = 1;
 constexpr int kTile = kThreads * kPointsPerThread;
 constexpr int kAcc = 32;     // accumulator slots per partial record (29 used)
-constexpr int kMinBlocksPerSM = 2;
+constexpr int kMinBlocksPerSM = 1;
 
 enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
 
@@ -239,8 +239,156 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The fused kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
+// Per-correspondence arithmetic (shared by the VGICP and GICP kernels).
+//   u = R p (rotated source point), t = translation, (mb, b**) = target mean / covariance, a** = source covariance,
+//   RL = rotation of the linearization point (== R when linearizing).
 // ---------------------------------------------------------------------------------------------------------------
+struct TargetRec {
+  double2 r01, r23, r45, r67, r89;  // mean(3) | cov upper(6) | count
+};
+struct SourceCov {
+  double a00, a01, a02, a11, a12, a22;
+};
+
+__device__ __forceinline__ TargetRec load_record(const double* __restrict__ records, int id) {
+  const double2* rec = reinterpret_cast<const double2*>(records + static_cast<size_t>(id < 0 ? 0 : id) * kRecordDoubles);
+  TargetRec r;
+  r.r01 = __ldg(rec);
+  r.r23 = __ldg(rec + 1);
+  r.r45 = __ldg(rec + 2);
+  r.r67 = __ldg(rec + 3);
+  r.r89 = __ldg(rec + 4);
+  return r;
+}
+
+template <typename CT>
+__device__ __forceinline__ SourceCov load_cov(const CT* __restrict__ cv, size_t n_pad, uint32_t i) {
+  SourceCov c;
+  c.a00 = ldv(cv, i);
+  c.a01 = ldv(cv + n_pad, i);
+  c.a02 = ldv(cv + 2 * n_pad, i);
+  c.a11 = ldv(cv + 3 * n_pad, i);
+  c.a12 = ldv(cv + 4 * n_pad, i);
+  c.a22 = ldv(cv + 5 * n_pad, i);
+  return c;
+}
+
+template <int MODE>
+__device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const double (&RL)[9], const double (&t)[3], double v0, double v1, double v2,
+                                                 const TargetRec& T, const SourceCov& A) {
+  const double mb0 = T.r01.x, mb1 = T.r01.y, mb2 = T.r23.x;
+  const double b00 = T.r23.y, b01 = T.r45.x, b02 = T.r45.y, b11 = T.r67.x, b12 = T.r67.y, b22 = T.r89.x;
+  // fused covariance S = C_B + RL C_A RL^T (symmetric), M = S^-1 (cofactors / det)
+  const double t00 = RL[0] * A.a00 + RL[1] * A.a01 + RL[2] * A.a02;
+  const double t01 = RL[0] * A.a01 + RL[1] * A.a11 + RL[2] * A.a12;
+  const double t02 = RL[0] * A.a02 + RL[1] * A.a12 + RL[2] * A.a22;
+  const double s00 = b00 + (t00 * RL[0] + t01 * RL[1] + t02 * RL[2]);
+  const double s01 = b01 + (t00 * RL[3] + t01 * RL[4] + t02 * RL[5]);
+  const double s02 = b02 + (t00 * RL[6] + t01 * RL[7] + t02 * RL[8]);
+  const double t10 = RL[3] * A.a00 + RL[4] * A.a01 + RL[5] * A.a02;
+  const double t11 = RL[3] * A.a01 + RL[4] * A.a11 + RL[5] * A.a12;
+  const double t12 = RL[3] * A.a02 + RL[4] * A.a12 + RL[5] * A.a22;
+  const double s11 = b11 + (t10 * RL[3] + t11 * RL[4] + t12 * RL[5]);
+  const double s12 = b12 + (t10 * RL[6] + t11 * RL[7] + t12 * RL[8]);
+  const double t20 = RL[6] * A.a00 + RL[7] * A.a01 + RL[8] * A.a02;
+  const double t21 = RL[6] * A.a01 + RL[7] * A.a11 + RL[8] * A.a12;
+  const double t22 = RL[6] * A.a02 + RL[7] * A.a12 + RL[8] * A.a22;
+  const double s22 = b22 + (t20 * RL[6] + t21 * RL[7] + t22 * RL[8]);
+
+  const double c00 = s11 * s22 - s12 * s12;
+  const double c01 = s02 * s12 - s01 * s22;
+  const double c02 = s01 * s12 - s02 * s11;
+  const double c11 = s00 * s22 - s02 * s02;
+  const double c12 = s01 * s02 - s00 * s12;
+  const double c22 = s00 * s11 - s01 * s01;
+  const double inv_det = 1.0 / (s00 * c00 + s01 * c01 + s02 * c02);
+  const double m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
+  const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
+
+  // residual r = mean_B - (u + t), Mahalanobis error
+  const double e0 = mb0 - __dadd_rn(v0, t[0]), e1 = mb1 - __dadd_rn(v1, t[1]), e2 = mb2 - __dadd_rn(v2, t[2]);
+  const double w0 = m00 * e0 + m01 * e1 + m02 * e2;
+  const double w1 = m01 * e0 + m11 * e1 + m12 * e2;
+  const double w2 = m02 * e0 + m12 * e1 + m22 * e2;
+  acc[27] += e0 * w0 + e1 * w1 + e2 * w2;
+  acc[28] += 1.0;
+
+  if (MODE == MODE_LINEARIZE) {
+    // K = hat(u) M  (column j = u x M[:,j])
+    const double k00 = v1 * m02 - v2 * m01, k10 = v2 * m00 - v0 * m02, k20 = v0 * m01 - v1 * m00;
+    const double k01 = v1 * m12 - v2 * m11, k11 = v2 * m01 - v0 * m12, k21 = v0 * m11 - v1 * m01;
+    const double k02 = v1 * m22 - v2 * m12, k12 = v2 * m02 - v0 * m22, k22 = v0 * m12 - v1 * m02;
+    // A_rr = K hat(u)^T
+    acc[0] += k02 * v1 - k01 * v2;
+    acc[1] += k00 * v2 - k02 * v0;
+    acc[2] += k01 * v0 - k00 * v1;
+    acc[3] += k10 * v2 - k12 * v0;
+    acc[4] += k11 * v0 - k10 * v1;
+    acc[5] += k21 * v0 - k20 * v1;
+    acc[6] += k00;
+    acc[7] += k01;
+    acc[8] += k02;
+    acc[9] += k10;
+    acc[10] += k11;
+    acc[11] += k12;
+    acc[12] += k20;
+    acc[13] += k21;
+    acc[14] += k22;
+    acc[15] += m00;
+    acc[16] += m01;
+    acc[17] += m02;
+    acc[18] += m11;
+    acc[19] += m12;
+    acc[20] += m22;
+    // c_r = u x (M r), c_t = M r
+    acc[21] += v1 * w2 - v2 * w1;
+    acc[22] += v2 * w0 - v0 * w2;
+    acc[23] += v0 * w1 - v1 * w0;
+    acc[24] += w0;
+    acc[25] += w1;
+    acc[26] += w2;
+  }
+}
+
+// u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
+__device__ __forceinline__ void rotate_point(const double (&R)[9], double x, double y, double z, double& u0, double& u1, double& u2) {
+  u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
+  u1 = __dadd_rn(__dadd_rn(__dmul_rn(R[3], x), __dmul_rn(R[4], y)), __dmul_rn(R[5], z));
+  u2 = __dadd_rn(__dadd_rn(__dmul_rn(R[6], x), __dmul_rn(R[7], y)), __dmul_rn(R[8], z));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fused kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
+//
+// A CTA takes tiles c, c+G, c+2G, ... (G = grid size); tiles of one factor are contiguous, so the CTA meets a factor
+// in one run of J tiles, thread `tid` owning element `tid` of each.  For VGICP the run is SOFTWARE-PIPELINED in
+// registers: a correspondence is the dependent chain  coordinates -> bucket group -> voxel record -> arithmetic, and the
+// 29 float64 accumulators leave room for only 8 warps per SM, so instead of hiding the chain behind other warps every
+// thread keeps the loads of its next three points in flight while it does the arithmetic of the current one:
+//     iteration j:  S0(j+3) issue coordinate loads        S1(j+2) rotate, floor, hash, issue bucket-group loads
+//                   S2(j+1) match -> voxel id, issue record + covariance loads        S3(j) arithmetic
+// ---------------------------------------------------------------------------------------------------------------
+template <typename PT>
+struct StageXYZ {  // S0 result: coordinates in flight
+  PT x, y, z;
+  uint32_t i;
+  int id;  // error mode: correspondence frozen at the last linearize (loaded with the coordinates); -1 when out of range
+};
+struct StageProbe {  // S1 result: bucket group in flight
+  double u0, u1, u2;
+  int cx, cy, cz;
+  uint32_t g;
+  uint32_t i;
+  int id;
+  BucketGroup grp;
+};
+struct StageGather {  // S2 result: target record + source covariance in flight
+  double u0, u1, u2;
+  int id;
+  TargetRec T;
+  SourceCov A;
+};
+
 template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
@@ -253,19 +401,19 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
   double acc[kAcc];
   // pose at which residuals / Jacobians are evaluated (R, t) and rotation of the linearization point (Rl) for the fused covariance
   double R[9], t[3], Rl_[9];
-  int cur = -1;
 
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += G) {
+  uint32_t tile = blockIdx.x;
+  while (tile < num_tiles) {
     const int f = static_cast<int>(__ldg(tile_factor + tile));
-    if (f != cur) {
-      if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
-      __syncthreads();
-      if (tid < static_cast<int>(sizeof(FactorDesc) / 4)) {
-        reinterpret_cast<uint32_t*>(&sh.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + tid);
-      }
-      __syncthreads();
-      const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(sh.desc.out_index) * 16;
-      const double* pl = poses_lin + static_cast<size_t>(sh.desc.out_index) * 16;
+    __syncthreads();
+    if (tid < static_cast<int>(sizeof(FactorDesc) / 4)) {
+      reinterpret_cast<uint32_t*>(&sh.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + tid);
+    }
+    __syncthreads();
+    const FactorDesc& d = sh.desc;
+    {
+      const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16;
+      const double* pl = poses_lin + static_cast<size_t>(d.out_index) * 16;
 #pragma unroll
       for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -275,132 +423,112 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         }
         t[r] = __ldg(pe + r * 4 + 3);
       }
-#pragma unroll
-      for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
-      cur = f;
     }
+#pragma unroll
+    for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
 
-    const FactorDesc& d = sh.desc;
     const uint32_t n = d.n;
     const size_t n_pad = d.n_pad;
     const PT* __restrict__ px = static_cast<const PT*>(d.pts);
     const CT* __restrict__ cv = static_cast<const CT*>(d.covs);
-    const uint32_t base = (tile - d.tile_begin) * kTile;
+    const uint32_t tile_end = d.tile_begin + d.num_tiles;
+    const uint32_t J = (tile_end - tile + G - 1) / G;  // tiles of this factor owned by this CTA
+    const uint32_t base0 = (tile - d.tile_begin) * kTile + tid;
+    const uint32_t stride = G * kTile;
+    const double(&RL)[9] = (MODE == MODE_ERROR) ? Rl_ : R;
 
-#pragma unroll
-    for (int k = 0; k < kPointsPerThread; k++) {
-      const uint32_t i = base + k * kThreads + tid;
-      if (i >= n) continue;
-
-      const double x = ldv(px, i), y = ldv(px + n_pad, i), z = ldv(px + 2 * n_pad, i);
-      // u = R p, q = u + t : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU path)
-      const double u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
-      const double u1 = __dadd_rn(__dadd_rn(__dmul_rn(R[3], x), __dmul_rn(R[4], y)), __dmul_rn(R[5], z));
-      const double u2 = __dadd_rn(__dadd_rn(__dmul_rn(R[6], x), __dmul_rn(R[7], y)), __dmul_rn(R[8], z));
-      const double q0 = __dadd_rn(u0, t[0]), q1 = __dadd_rn(u1, t[1]), q2 = __dadd_rn(u2, t[2]);
-
-      // ---- correspondence ----
-      int id;
-      if (MODE == MODE_LINEARIZE) {
-        if (KIND == 0) {
-          id = lookup_voxel(d.buckets, d.bucket_mask, voxel_coord1(q0, d.inv_leaf), voxel_coord1(q1, d.inv_leaf), voxel_coord1(q2, d.inv_leaf));
-        } else {
-          const KdTreeView tv{d.nodes, d.leaf_pts, d.leaf_pts + d.leaf_n_pad, d.leaf_pts + 2 * static_cast<size_t>(d.leaf_n_pad)};
-          double sq;
-          id = kdtree_nn1(tv, q0, q1, q2, d.max_sq, &sq);
+    if (KIND == 0) {
+      // ------------------------------------------- VGICP: register software pipeline -------------------------------------------
+      auto s0 = [&](uint32_t j) {
+        StageXYZ<PT> a;
+        const uint32_t i = base0 + j * stride;
+        const bool ok = j < J && i < n;
+        a.i = ok ? i : 0u;  // out-of-range lanes read element 0 (always allocated) and are masked through id = -1
+        a.x = __ldg(px + a.i);
+        a.y = __ldg(px + n_pad + a.i);
+        a.z = __ldg(px + 2 * n_pad + a.i);
+        a.id = ok ? 0 : -1;
+        if (MODE == MODE_ERROR) a.id = ok ? __ldg(d.corr + a.i) : -1;
+        return a;
+      };
+      auto s1 = [&](const StageXYZ<PT>& a) {
+        StageProbe b;
+        rotate_point(R, static_cast<double>(a.x), static_cast<double>(a.y), static_cast<double>(a.z), b.u0, b.u1, b.u2);
+        b.i = a.i;
+        b.id = a.id;
+        if (MODE == MODE_LINEARIZE) {
+          b.cx = voxel_coord1(__dadd_rn(b.u0, t[0]), d.inv_leaf);
+          b.cy = voxel_coord1(__dadd_rn(b.u1, t[1]), d.inv_leaf);
+          b.cz = voxel_coord1(__dadd_rn(b.u2, t[2]), d.inv_leaf);
+          b.g = voxel_hash(b.cx, b.cy, b.cz) & d.bucket_mask;
+          b.grp = load_group(d.buckets, b.g);
         }
-        d.corr[i] = id;
-      } else {
-        id = __ldg(d.corr + i);  // frozen at the last linearize
+        return b;
+      };
+      auto s2 = [&](const StageProbe& b) {
+        StageGather c;
+        c.u0 = b.u0;
+        c.u1 = b.u1;
+        c.u2 = b.u2;
+        c.id = b.id;
+        if (MODE == MODE_LINEARIZE) {
+          int r = match_group(b.grp, b.cx, b.cy, b.cz);
+          uint32_t g = b.g;
+          while (r == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
+            g = (g + 1) & d.bucket_mask;
+            r = match_group(load_group(d.buckets, g), b.cx, b.cy, b.cz);
+          }
+          if (b.id >= 0) {
+            c.id = r;
+            d.corr[b.i] = r;
+          }
+        }
+        c.T = load_record(d.records, c.id);
+        c.A = load_cov(cv, n_pad, b.i);
+        return c;
+      };
+
+      // prologue: fill the pipeline
+      StageXYZ<PT> a0 = s0(0), a1 = s0(1), a2 = s0(2);
+      StageProbe b0 = s1(a0), b1 = s1(a1);
+      StageGather cur = s2(b0);
+      StageProbe nxt1 = b1;
+      StageXYZ<PT> nxt2 = a2;
+      for (uint32_t j = 0; j < J; j++) {
+        const StageXYZ<PT> in0 = s0(j + 3);
+        const StageProbe in1 = s1(nxt2);
+        const StageGather in2 = s2(nxt1);
+        if (cur.id >= 0) accumulate_point<MODE>(acc, RL, t, cur.u0, cur.u1, cur.u2, cur.T, cur.A);
+        cur = in2;
+        nxt1 = in1;
+        nxt2 = in0;
       }
-      if (id < 0) continue;
-
-      // ---- gather target record: mean(3) cov(6) ----
-      const double2* rec = reinterpret_cast<const double2*>(d.records + static_cast<size_t>(id) * kRecordDoubles);
-      const double2 r01 = __ldg(rec), r23 = __ldg(rec + 1), r45 = __ldg(rec + 2), r67 = __ldg(rec + 3), r89 = __ldg(rec + 4);
-      const double mb0 = r01.x, mb1 = r01.y, mb2 = r23.x;
-      const double b00 = r23.y, b01 = r45.x, b02 = r45.y, b11 = r67.x, b12 = r67.y, b22 = r89.x;
-
-      const double a00 = ldv(cv, i), a01 = ldv(cv + n_pad, i), a02 = ldv(cv + 2 * n_pad, i);
-      const double a11 = ldv(cv + 3 * n_pad, i), a12 = ldv(cv + 4 * n_pad, i), a22 = ldv(cv + 5 * n_pad, i);
-
-      // ---- fused covariance S = C_B + Rl C_A Rl^T (symmetric), M = S^-1 ----
-      double s00, s01, s02, s11, s12, s22;
-      {
-#define Rl(k) (MODE == MODE_ERROR ? Rl_[k] : R[k])
-        const double t00 = Rl(0) * a00 + Rl(1) * a01 + Rl(2) * a02;
-        const double t01 = Rl(0) * a01 + Rl(1) * a11 + Rl(2) * a12;
-        const double t02 = Rl(0) * a02 + Rl(1) * a12 + Rl(2) * a22;
-        s00 = b00 + (t00 * Rl(0) + t01 * Rl(1) + t02 * Rl(2));
-        s01 = b01 + (t00 * Rl(3) + t01 * Rl(4) + t02 * Rl(5));
-        s02 = b02 + (t00 * Rl(6) + t01 * Rl(7) + t02 * Rl(8));
-        const double t10 = Rl(3) * a00 + Rl(4) * a01 + Rl(5) * a02;
-        const double t11 = Rl(3) * a01 + Rl(4) * a11 + Rl(5) * a12;
-        const double t12 = Rl(3) * a02 + Rl(4) * a12 + Rl(5) * a22;
-        s11 = b11 + (t10 * Rl(3) + t11 * Rl(4) + t12 * Rl(5));
-        s12 = b12 + (t10 * Rl(6) + t11 * Rl(7) + t12 * Rl(8));
-        const double t20 = Rl(6) * a00 + Rl(7) * a01 + Rl(8) * a02;
-        const double t21 = Rl(6) * a01 + Rl(7) * a11 + Rl(8) * a12;
-        const double t22 = Rl(6) * a02 + Rl(7) * a12 + Rl(8) * a22;
-        s22 = b22 + (t20 * Rl(6) + t21 * Rl(7) + t22 * Rl(8));
-#undef Rl
-      }
-      const double c00 = s11 * s22 - s12 * s12;
-      const double c01 = s02 * s12 - s01 * s22;
-      const double c02 = s01 * s12 - s02 * s11;
-      const double c11 = s00 * s22 - s02 * s02;
-      const double c12 = s01 * s02 - s00 * s12;
-      const double c22 = s00 * s11 - s01 * s01;
-      const double inv_det = 1.0 / (s00 * c00 + s01 * c01 + s02 * c02);
-      const double m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
-      const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
-
-      // ---- residual, Mahalanobis error ----
-      const double e0 = mb0 - q0, e1 = mb1 - q1, e2 = mb2 - q2;
-      const double w0 = m00 * e0 + m01 * e1 + m02 * e2;
-      const double w1 = m01 * e0 + m11 * e1 + m12 * e2;
-      const double w2 = m02 * e0 + m12 * e1 + m22 * e2;
-      acc[27] += e0 * w0 + e1 * w1 + e2 * w2;
-      acc[28] += 1.0;
-
-      if (MODE == MODE_LINEARIZE) {
-        // K = hat(u) M  (column j = u x M[:,j])
-        const double k00 = u1 * m02 - u2 * m01, k10 = u2 * m00 - u0 * m02, k20 = u0 * m01 - u1 * m00;
-        const double k01 = u1 * m12 - u2 * m11, k11 = u2 * m01 - u0 * m12, k21 = u0 * m11 - u1 * m01;
-        const double k02 = u1 * m22 - u2 * m12, k12 = u2 * m02 - u0 * m22, k22 = u0 * m12 - u1 * m02;
-        // A_rr = K hat(u)^T
-        acc[0] += k02 * u1 - k01 * u2;
-        acc[1] += k00 * u2 - k02 * u0;
-        acc[2] += k01 * u0 - k00 * u1;
-        acc[3] += k10 * u2 - k12 * u0;
-        acc[4] += k11 * u0 - k10 * u1;
-        acc[5] += k21 * u0 - k20 * u1;
-        acc[6] += k00;
-        acc[7] += k01;
-        acc[8] += k02;
-        acc[9] += k10;
-        acc[10] += k11;
-        acc[11] += k12;
-        acc[12] += k20;
-        acc[13] += k21;
-        acc[14] += k22;
-        acc[15] += m00;
-        acc[16] += m01;
-        acc[17] += m02;
-        acc[18] += m11;
-        acc[19] += m12;
-        acc[20] += m22;
-        // c_r = u x (M r), c_t = M r
-        acc[21] += u1 * w2 - u2 * w1;
-        acc[22] += u2 * w0 - u0 * w2;
-        acc[23] += u0 * w1 - u1 * w0;
-        acc[24] += w0;
-        acc[25] += w1;
-        acc[26] += w2;
+    } else {
+      // ------------------------------------------- GICP: kd-tree 1-NN per point -------------------------------------------
+      const KdTreeView tv{d.nodes, d.leaf_pts, d.leaf_pts + d.leaf_n_pad, d.leaf_pts + 2 * static_cast<size_t>(d.leaf_n_pad)};
+      for (uint32_t j = 0; j < J; j++) {
+        const uint32_t i = base0 + j * stride;
+        if (i >= n) continue;
+        double u0, u1, u2;
+        rotate_point(R, ldv(px, i), ldv(px + n_pad, i), ldv(px + 2 * n_pad, i), u0, u1, u2);
+        int id;
+        if (MODE == MODE_LINEARIZE) {
+          double sq;
+          id = kdtree_nn1(tv, __dadd_rn(u0, t[0]), __dadd_rn(u1, t[1]), __dadd_rn(u2, t[2]), d.max_sq, &sq);
+          d.corr[i] = id;
+        } else {
+          id = __ldg(d.corr + i);
+        }
+        if (id < 0) continue;
+        const TargetRec T = load_record(d.records, id);
+        const SourceCov A = load_cov(cv, n_pad, i);
+        accumulate_point<MODE>(acc, RL, t, u0, u1, u2, T, A);
       }
     }
+
+    flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
+    tile += J * G;
   }
-  if (cur >= 0) flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -676,7 +804,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       d.n_pad = static_cast<uint32_t>(f->source->n_pad);
       if (f->kind == B2_FACTOR_VGICP) {
         d.buckets = f->voxelmap->d_buckets;
-        d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets - 1);
+        d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets / kGroup - 1);  // group mask
         d.inv_leaf = f->voxelmap->inv_resolution;
         d.records = f->voxelmap->d_records;
       } else {

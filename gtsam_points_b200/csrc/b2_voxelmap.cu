@@ -122,16 +122,19 @@ __global__ void insert_buckets_kernel(const int32_t* __restrict__ coords, size_t
   const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (r >= num_voxels) return;
   const int x = coords[r * 3], y = coords[r * 3 + 1], z = coords[r * 3 + 2];
-  uint32_t h = voxel_hash(x, y, z) & mask;
+  uint32_t g = voxel_hash(x, y, z) & mask;  // mask = number of groups - 1
   while (true) {
-    // all keys are distinct: claim the first empty bucket, nobody needs to compare against a half-written key
-    if (atomicCAS(&buckets[h].id, -1, static_cast<int>(r)) == -1) {
-      buckets[h].x = x;
-      buckets[h].y = y;
-      buckets[h].z = z;
-      return;
+    // all keys are distinct: claim the first empty slot of the first non-full group; nobody compares against a half-written key
+    for (int k = 0; k < kGroup; k++) {
+      VoxelBucket* b = buckets + static_cast<size_t>(g) * kGroup + k;
+      if (atomicCAS(&b->id, -1, static_cast<int>(r)) == -1) {
+        b->x = x;
+        b->y = y;
+        b->z = z;
+        return;
+      }
     }
-    h = (h + 1) & mask;
+    g = (g + 1) & mask;
   }
 }
 
@@ -145,7 +148,8 @@ __global__ void lookup_points_kernel(const double* __restrict__ pts, int pstride
   out[i] = lookup_voxel(buckets, mask, x, y, z);
 }
 
-size_t bucket_count_for(size_t num_voxels) { return static_cast<size_t>(next_pow2(std::max<uint64_t>(16, 2 * static_cast<uint64_t>(num_voxels)))); }
+// load factor <= 0.25 (see b2_device.cuh: one-round-trip lookups)
+size_t bucket_count_for(size_t num_voxels) { return static_cast<size_t>(next_pow2(std::max<uint64_t>(64, 4 * static_cast<uint64_t>(num_voxels)))); }
 
 b2_status alloc_map(b2_ctx* ctx, double resolution, size_t V, b2_voxelmap** out) {
   b2_voxelmap* vm = new b2_voxelmap;
@@ -186,19 +190,25 @@ b2_status b2_voxelmap_create_from_voxels(b2_ctx* ctx, double resolution, const i
 
   // host-side table build in id order (deterministic placement), duplicate coordinates rejected
   const size_t nb = bucket_count_for(V);
-  const uint32_t mask = static_cast<uint32_t>(nb - 1);
+  const uint32_t gmask = static_cast<uint32_t>(nb / kGroup - 1);
   std::vector<VoxelBucket> buckets(nb, VoxelBucket{-1, -1, -1, -1});
   std::vector<double> records(std::max<size_t>(V, 1) * kRecordDoubles, 0.0);
   for (size_t r = 0; r < V; r++) {
     const int x = coords[r * 3], y = coords[r * 3 + 1], z = coords[r * 3 + 2];
-    uint32_t h = voxel_hash(x, y, z) & mask;
-    while (buckets[h].id >= 0) {
-      if (buckets[h].x == x && buckets[h].y == y && buckets[h].z == z) {
-        return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_create_from_voxels: duplicate voxel coordinate (%d, %d, %d) at ids %d and %zu", x, y, z, buckets[h].id, r);
+    uint32_t g = voxel_hash(x, y, z) & gmask;
+    bool placed = false;
+    while (!placed) {
+      for (int k = 0; k < kGroup && !placed; k++) {
+        VoxelBucket& b = buckets[static_cast<size_t>(g) * kGroup + k];
+        if (b.id < 0) {
+          b = VoxelBucket{x, y, z, static_cast<int32_t>(r)};
+          placed = true;
+        } else if (b.x == x && b.y == y && b.z == z) {
+          return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_create_from_voxels: duplicate voxel coordinate (%d, %d, %d) at ids %d and %zu", x, y, z, b.id, r);
+        }
       }
-      h = (h + 1) & mask;
+      g = (g + 1) & gmask;
     }
-    buckets[h] = VoxelBucket{x, y, z, static_cast<int32_t>(r)};
     double* rec = &records[r * kRecordDoubles];
     for (int k = 0; k < 3; k++) rec[k] = means[r * 3 + k];
     const double* c = covs + r * 9;
@@ -310,7 +320,7 @@ b2_status b2_voxelmap_create_from_points(b2_ctx* ctx, double resolution, const d
     b2_voxelmap_destroy(vm);
     return fail(B2_ERR_CUDA, "b2_voxelmap_create_from_points: %s", cudaGetErrorString(e));
   }
-  insert_buckets_kernel<<<vgrid, 128, 0, st>>>(vm->d_coords, V, vm->d_buckets, static_cast<uint32_t>(vm->num_buckets - 1));
+  insert_buckets_kernel<<<vgrid, 128, 0, st>>>(vm->d_coords, V, vm->d_buckets, static_cast<uint32_t>(vm->num_buckets / kGroup - 1));
   if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) {
     b2_voxelmap_destroy(vm);
     return fail(B2_ERR_CUDA, "b2_voxelmap_create_from_points: %s", cudaGetErrorString(e));
@@ -377,7 +387,7 @@ b2_status b2_voxelmap_lookup(const b2_voxelmap* vm, const double* points, int po
   B2_CUDA(cudaMalloc(&di.p, n * sizeof(int32_t)));
   B2_CUDA(cudaMemcpyAsync(dp.p, points, n * point_stride * sizeof(double), cudaMemcpyHostToDevice, st));
   lookup_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(dp.as<double>(), point_stride, n, vm->inv_resolution, vm->d_buckets,
-                                                                              static_cast<uint32_t>(vm->num_buckets - 1), di.as<int32_t>());
+                                                                              static_cast<uint32_t>(vm->num_buckets / kGroup - 1), di.as<int32_t>());
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaMemcpyAsync(out_index, di.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
