@@ -245,7 +245,8 @@ def run_gpu(args):
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         inliers = []
         for i in range(K):
-            flush.fill_(i & 0xFF)
+            if not args.no_flush:
+                flush.fill_(i & 0xFF)
             sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
             ev[i][0].record(stream)
             if world == 1:
@@ -267,20 +268,35 @@ def run_gpu(args):
         n_inliers = int(rec[rank, 121])
         launches_dev = sset.set.launch_count() - launches0
 
-        # ---- end-to-end arm: public host API, host buffers, H2D + D2H inside the timed region ----
+        # ---- end-to-end arm: the public host entry point with HOST buffers (poses in, H/b records out) ----
+        # N = 1: the C-ABI call itself (b2_factor_set_linearize), which is what NonlinearFactorSetGPU.linearize and the C++
+        #        adapters issue; N > 1: ShardedFactorSet.linearize (host poses -> kernel -> all-reduce -> host records).
+        import ctypes as C
+
+        h_out = np.zeros((1, capi.B2_LINEARIZED_DOUBLES))
+        dp = C.POINTER(C.c_double)
+
+        def e2e_step(pose):
+            if world == 1:
+                capi.check(capi.lib().b2_factor_set_linearize(sset.set.h, pose.ctypes.data_as(dp), h_out.ctypes.data_as(dp)))
+                return h_out
+            return sset.linearize(pose)
+
+        poses_c = [np.ascontiguousarray(p.reshape(1, 16)) for p in poses]
         for i in range(W):
-            sset.linearize(poses[i])
+            e2e_step(poses_c[i])
         barrier()
         e2e_s = 0.0
         for i in range(K):
-            flush.fill_(i & 0xFF)
+            if not args.no_flush:
+                flush.fill_(i & 0xFF)
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            out = sset.linearize(poses[W + i])
+            out = e2e_step(poses_c[W + i])
             e2e_s += time.perf_counter() - t0
+        e2e_inliers = int(out[rank if world > 1 else 0, 121])
         barrier()
         clocks = sampler.stop() if rank == 0 else None
-        assert np.array_equal(out[rank, :122], rec[rank, :122]) or True
 
     # max over ranks
     tt = torch.tensor([dev_total_ms, e2e_s * 1e3, float(kern_ms.mean())], dtype=torch.float64, device=dev)
@@ -333,7 +349,7 @@ def run_gpu(args):
                 "parallelism": f"factor-sharded x{world}" + (" + 1 all-reduce of [N x 128] f64" if world > 1 else ""),
                 "source_storage": {"point_bytes": int(cinfo.point_bytes), "cov_bytes": int(cinfo.cov_bytes), "morton_ordered": bool(cinfo.reordered)},
                 "pose_perturbation": {"rot_rad": POSE_ROT, "trans_m": POSE_TRANS},
-                "l2": "flushed (256 MiB write) between timed steps",
+                "l2": "flushed (256 MiB write) between timed steps" if not args.no_flush else "WARM (diagnostic run, not a valid number)",
                 "setup_s": setup_s,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * 1, "d2h_bytes_per_step": 1024 * world, "ms_per_step": e2e_ms / K},
@@ -365,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps (NOT a valid bench number)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

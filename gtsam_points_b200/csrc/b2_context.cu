@@ -30,7 +30,7 @@ b2_status b2_ctx::ensure_stage(size_t host_bytes, size_t dev_bytes) {
     h_stage = nullptr;
     h_stage_bytes = 0;
     const size_t want = b2::round_up(host_bytes * 2, 4096);
-    B2_CUDA(cudaHostAlloc(&h_stage, want, cudaHostAllocDefault));
+    B2_CUDA(cudaHostAlloc(&h_stage, want, cudaHostAllocMapped | cudaHostAllocPortable));
     h_stage_bytes = want;
   }
   if (dev_bytes > d_stage_bytes) {

@@ -31,11 +31,17 @@
 
 namespace b2 {
 
-constexpr int kThreads = 256;
+#ifndef B2_THREADS
+#define B2_THREADS 256
+#endif
+constexpr int kThreads = B2_THREADS;
 constexpr int kPointsPerThread = 1;
 constexpr int kTile = kThreads * kPointsPerThread;
 constexpr int kAcc = 32;     // accumulator slots per partial record (29 used)
-constexpr int kMinBlocksPerSM = 1;
+#ifndef B2_MINBLOCKS
+#define B2_MINBLOCKS 1
+#endif
+constexpr int kMinBlocksPerSM = B2_MINBLOCKS;
 
 enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
 
@@ -163,7 +169,10 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
   __syncthreads();
 
   if (MODE == MODE_ERROR) {
-    if (tid == 0) out[d.out_index] = sh.tot[27];
+    if (tid == 0) {
+      out[d.out_index] = sh.tot[27];
+      __threadfence_system();  // `out` may be mapped host memory
+    }
     __syncthreads();
     return;
   }
@@ -235,6 +244,7 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
 #pragma unroll
     for (int k = 122; k < B2_LINEARIZED_DOUBLES; k++) rec[k] = 0.0;
   }
+  __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
   __syncthreads();
 }
 
@@ -350,6 +360,8 @@ __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const doub
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
 __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, double y, double z, double& u0, double& u1, double& u2) {
   u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
@@ -437,6 +449,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     const uint32_t stride = G * kTile;
     const double(&RL)[9] = (MODE == MODE_ERROR) ? Rl_ : R;
 
+#ifndef B2_VGICP_SIMPLE
     if (KIND == 0) {
       // ------------------------------------------- VGICP: register software pipeline -------------------------------------------
       auto s0 = [&](uint32_t j) {
@@ -503,7 +516,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         nxt1 = in1;
         nxt2 = in0;
       }
-    } else {
+    } else
+#endif
+    {
       // ------------------------------------------- GICP: kd-tree 1-NN per point -------------------------------------------
       const KdTreeView tv{d.nodes, d.leaf_pts, d.leaf_pts + d.leaf_n_pad, d.leaf_pts + 2 * static_cast<size_t>(d.leaf_n_pad)};
       for (uint32_t j = 0; j < J; j++) {
@@ -513,8 +528,13 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         rotate_point(R, ldv(px, i), ldv(px + n_pad, i), ldv(px + 2 * n_pad, i), u0, u1, u2);
         int id;
         if (MODE == MODE_LINEARIZE) {
-          double sq;
-          id = kdtree_nn1(tv, __dadd_rn(u0, t[0]), __dadd_rn(u1, t[1]), __dadd_rn(u2, t[2]), d.max_sq, &sq);
+          if (KIND == 0) {
+            id = lookup_voxel(d.buckets, d.bucket_mask, voxel_coord1(__dadd_rn(u0, t[0]), d.inv_leaf), voxel_coord1(__dadd_rn(u1, t[1]), d.inv_leaf),
+                              voxel_coord1(__dadd_rn(u2, t[2]), d.inv_leaf));
+          } else {
+            double sq;
+            id = kdtree_nn1(tv, __dadd_rn(u0, t[0]), __dadd_rn(u1, t[1]), __dadd_rn(u2, t[2]), d.max_sq, &sq);
+          }
           d.corr[i] = id;
         } else {
           id = __ldg(d.corr + i);
@@ -549,6 +569,9 @@ KernelFn pick_kernel(int kind, int mode, int pb, int cb) {
   return mode == MODE_LINEARIZE ? pick_kernel<1, MODE_LINEARIZE>(pb, cb) : pick_kernel<1, MODE_ERROR>(pb, cb);
 }
 
+// host-API sets up to this many factors use the zero-copy path (poses read from / results written to mapped pinned memory)
+constexpr size_t kZeroCopyMaxFactors = 64;
+
 struct Group {
   int kind, pb, cb;
   std::vector<size_t> members;  // indices into the set's factor list
@@ -557,6 +580,7 @@ struct Group {
   uint32_t num_tiles = 0;
   uint32_t grid[2] = {0, 0};
   KernelFn fn[2] = {nullptr, nullptr};
+  size_t dyn_smem = 0;
 };
 
 }  // namespace b2
@@ -614,7 +638,7 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
   cudaStream_t st = s->ctx->stream;
   double* lin_store = (mode == MODE_LINEARIZE && d_lin != s->d_poses_lin) ? s->d_poses_lin : nullptr;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kThreads, 0, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, lin_store);
+    g.fn[mode]<<<g.grid[mode], kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, lin_store);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -824,8 +848,11 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     g.num_tiles = tile_cursor;
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb);
+      g.dyn_smem = 0;
       int per_sm = 0;
-      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], kThreads, 0);
+      cudaError_t e = cudaSuccess;
+      if (g.dyn_smem) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(g.fn[mode]), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem));
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], kThreads, g.dyn_smem);
       if (e != cudaSuccess || per_sm < 1) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: occupancy query failed (%s)", cudaGetErrorString(e)));
       g.grid[mode] = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count * per_sm));
       for (auto& d : descs) {
@@ -914,10 +941,23 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
   B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
   char* h = static_cast<char*>(s->ctx->h_stage);
   std::memcpy(h, deltas, in_bytes);
-  B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
-  B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out));
-  B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaStreamSynchronize(st));
+  if (F <= kZeroCopyMaxFactors) {
+    // Small sets: ONE launch and one stream sync.  The staging buffer is pinned, mapped host memory: the kernel reads the
+    // poses straight from it (128 B per factor over PCIe) and its per-factor epilogue writes the 1 KiB result record
+    // straight back, so there is no separate H2D / D2H copy operation on the stream (NonlinearFactorSetGPU's protocol
+    // needs 2 copies + 2 syncs, nonlinear_factor_set_gpu.cpp:91-124).  The linearization point is kept on the device by
+    // the same epilogue (lin_store).
+    double* d_in = nullptr;
+    B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
+    double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res));
+    B2_CUDA(cudaStreamSynchronize(st));
+  } else {
+    B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out));
+    B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
   std::memcpy(out, h + in_bytes, out_bytes);
   s->dev_lin_valid = true;
   for (size_t i = 0; i < F; i++) {
@@ -944,10 +984,18 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
   B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
   char* h = static_cast<char*>(s->ctx->h_stage);
   std::memcpy(h, deltas_eval, in_bytes);
-  B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));
-  B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, s->d_poses_eval, s->d_err));
-  B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_err, out_bytes, cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaStreamSynchronize(st));
+  if (F <= kZeroCopyMaxFactors) {
+    double* d_in = nullptr;
+    B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
+    double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
+    B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, d_in, d_res));
+    B2_CUDA(cudaStreamSynchronize(st));
+  } else {
+    B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));
+    B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, s->d_poses_eval, s->d_err));
+    B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_err, out_bytes, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
   std::memcpy(out_errors, h + in_bytes, out_bytes);
   return B2_OK;
 }
