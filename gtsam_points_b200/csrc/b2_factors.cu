@@ -64,6 +64,7 @@ struct FactorDesc {
   // mean(3) | cov(6) | count records: voxels (id order) or target points (leaf order)
   const double* records;
   int32_t* corr;
+  double* lin_pose;  // per-factor linearization point (16 doubles, row-major 4x4), owned by the factor
   uint32_t tile_begin;
   uint32_t num_tiles;
   uint32_t slot_begin[2];  // per mode
@@ -117,8 +118,7 @@ struct Shared {
 
 template <int MODE>
 __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], const double (&Rr)[9], const double (&tr)[3], double* __restrict__ partials,
-                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G, const double* __restrict__ poses_lin,
-                                             double* __restrict__ lin_store) {
+                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G, const double* __restrict__ poses_lin) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double w = warp_reduce32(v, lane);
   sh.red[warp][lane] = w;
@@ -236,8 +236,8 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
     rec[108 + i] = bt;
     rec[114 + i] = bs;
   } else if (tid >= 128 && tid < 144) {
-    // remember the linearization point on the device (error-only launches read it back); a different buffer than poses_lin
-    if (lin_store) lin_store[static_cast<size_t>(d.out_index) * 16 + (tid - 128)] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (tid - 128));
+    // remember the linearization point with the factor (error-only launches of ANY set read it back)
+    d.lin_pose[tid - 128] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (tid - 128));
   } else if (tid == 96) {
     rec[120] = sh.tot[27];
     rec[121] = sh.tot[28];
@@ -404,8 +404,7 @@ struct StageGather {  // S2 result: target record + source covariance in flight
 template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
-              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-              double* __restrict__ lin_store) {
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
   __shared__ Shared sh;
   const int tid = threadIdx.x;
   const uint32_t G = gridDim.x;
@@ -425,7 +424,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     const FactorDesc& d = sh.desc;
     {
       const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16;
-      const double* pl = poses_lin + static_cast<size_t>(d.out_index) * 16;
+      const double* pl = (MODE == MODE_ERROR) ? d.lin_pose : poses_lin + static_cast<size_t>(d.out_index) * 16;
 #pragma unroll
       for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -546,7 +545,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       }
     }
 
-    flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin, lin_store);
+    flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin);
     tile += J * G;
   }
 }
@@ -554,7 +553,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
 // ---------------------------------------------------------------------------------------------------------------
-using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, double*);
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*);
 
 template <int KIND, int MODE>
 KernelFn pick_kernel(int pb, int cb) {
@@ -597,7 +596,6 @@ struct b2_factor_set {
   double* d_poses_eval = nullptr;  // F x 16
   double* d_out = nullptr;         // F x 128
   double* d_err = nullptr;         // F
-  bool dev_lin_valid = false;      // d_poses_lin holds the linearization points of all factors
   uint64_t launches = 0;
 };
 
@@ -636,9 +634,8 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, 
 
 b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
   cudaStream_t st = s->ctx->stream;
-  double* lin_store = (mode == MODE_LINEARIZE && d_lin != s->d_poses_lin) ? s->d_poses_lin : nullptr;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, lin_store);
+    g.fn[mode]<<<g.grid[mode], kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -665,8 +662,9 @@ b2_status b2_vgicp_factor_create(b2_ctx* ctx, const b2_voxelmap* target, const b
   f->voxelmap = target;
   f->source = source;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&f->d_corr), std::max<size_t>(source->n_pad, 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&f->d_lin_pose), 16 * sizeof(double));
   if (e != cudaSuccess) {
-    delete f;
+    b2_factor_destroy(f);
     return fail(B2_ERR_OUT_OF_MEMORY, "b2_vgicp_factor_create: %s", cudaGetErrorString(e));
   }
   *out = f;
@@ -696,6 +694,7 @@ b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const
   cudaError_t e;
   uint32_t* d_inv = nullptr;
   if ((e = cudaMalloc(reinterpret_cast<void**>(&f->d_corr), std::max<size_t>(source->n_pad, 1) * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&f->d_lin_pose), 16 * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&f->d_target_records), std::max<size_t>(nt, 1) * kRecordDoubles * sizeof(double))) != cudaSuccess) {
     b2_factor_destroy(f);
     return fail(B2_ERR_OUT_OF_MEMORY, "b2_gicp_factor_create: %s", cudaGetErrorString(e));
@@ -736,6 +735,7 @@ b2_status b2_factor_destroy(b2_factor* f) {
   if (f->self_set) b2_factor_set_destroy(f->self_set);
   if (f->d_corr) cudaFree(f->d_corr);
   if (f->d_target_records) cudaFree(f->d_target_records);
+  if (f->d_lin_pose) cudaFree(f->d_lin_pose);
   delete f;
   return B2_OK;
 }
@@ -839,6 +839,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
         d.records = f->d_target_records;
       }
       d.corr = f->d_corr;
+      d.lin_pose = f->d_lin_pose;
       d.tile_begin = tile_cursor;
       d.num_tiles = std::max<uint32_t>(1u, (d.n + kTile - 1) / kTile);
       d.out_index = static_cast<uint32_t>(g.members[k]);
@@ -919,16 +920,16 @@ b2_status b2_factor_set_linearize_device(b2_factor_set* s, const double* d_delta
   (void)F;
   // one launch per group, nothing else: the kernel's per-factor epilogue also stores the linearization point on the device
   B2_TRY(launch_groups(s, MODE_LINEARIZE, d_deltas, d_deltas, d_out));
-  s->dev_lin_valid = true;
   for (auto* f : s->factors) f->linearized = true;
   return B2_OK;
 }
 
 b2_status b2_factor_set_error_device(b2_factor_set* s, const double* d_deltas_eval, double* d_out_errors) {
   B2_REQUIRE(s && d_deltas_eval && d_out_errors, "b2_factor_set_error_device: NULL argument");
-  if (!s->dev_lin_valid) return fail(B2_ERR_INVALID_STATE, "b2_factor_set_error_device: the set has not been linearized yet");
+  for (auto* f : s->factors)
+    if (!f->linearized) return fail(B2_ERR_INVALID_STATE, "b2_factor_set_error_device: a factor of the set has not been linearized yet");
   B2_CUDA(cudaSetDevice(s->ctx->device));
-  B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, d_deltas_eval, d_out_errors));
+  B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_deltas_eval, d_out_errors));
   return B2_OK;
 }
 
@@ -959,7 +960,6 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     B2_CUDA(cudaStreamSynchronize(st));
   }
   std::memcpy(out, h + in_bytes, out_bytes);
-  s->dev_lin_valid = true;
   for (size_t i = 0; i < F; i++) {
     s->factors[i]->linearized = true;
     std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
@@ -972,13 +972,13 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
   B2_CUDA(cudaSetDevice(s->ctx->device));
   cudaStream_t st = s->ctx->stream;
   const size_t F = s->factors.size();
-  if (!s->dev_lin_valid) {
-    // First evaluation before any linearization: the reference establishes the correspondences at the evaluation
-    // point (integrated_vgicp_factor_impl.hpp:183-185) -- i.e. a linearize at delta_eval whose error is returned.
-    std::vector<b2_linearized> lin(F);
-    B2_TRY(b2_factor_set_linearize(s, deltas_eval, lin.data()));
-    for (size_t i = 0; i < F; i++) out_errors[i] = lin[i].error;
-    return B2_OK;
+  // A factor evaluated before its first linearization establishes its correspondences at the evaluation point
+  // (integrated_vgicp_factor_impl.hpp:183-185): linearize exactly those factors, individually, at delta_eval first.
+  for (size_t i = 0; i < F; i++) {
+    if (!s->factors[i]->linearized) {
+      b2_linearized tmp;
+      B2_TRY(b2_factor_linearize(s->factors[i], deltas_eval + i * 16, &tmp));
+    }
   }
   const size_t in_bytes = F * 16 * sizeof(double), out_bytes = F * sizeof(double);
   B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
@@ -988,11 +988,11 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
     double* d_in = nullptr;
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
-    B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, d_in, d_res));
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res));
     B2_CUDA(cudaStreamSynchronize(st));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));
-    B2_TRY(launch_groups(s, MODE_ERROR, s->d_poses_lin, s->d_poses_eval, s->d_err));
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, s->d_poses_eval, s->d_err));
     B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_err, out_bytes, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
   }

@@ -133,6 +133,7 @@ struct b2_factor {
   double max_corr_sq = 1.0;
   int32_t* d_corr = nullptr;       // per stored source position: voxel id / target leaf position, -1 = none
   double* d_target_records = nullptr;  // GICP: target records in leaf order (Nt x 10), owned
+  double* d_lin_pose = nullptr;        // 16 doubles: the linearization point, written by the linearize kernel's epilogue
   bool linearized = false;
   double lin_delta[16] = {0};
   b2_factor_set* self_set = nullptr;  // lazily created set of size 1 for the single-factor entry points
