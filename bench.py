@@ -243,30 +243,37 @@ def run_gpu(args):
             sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        inliers = []
         for i in range(K):
             if not args.no_flush:
                 flush.fill_(i & 0xFF)
             sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
+            if world > 1:
+                barrier()  # ranks enter the timed step together: the collective must not absorb another rank's L2 flush
             ev[i][0].record(stream)
             if world == 1:
-                # single GPU: the step IS the kernel launch (no collective); same events serve the roofline
+                # single GPU: the step IS the kernel launch (no collective); the same events serve the roofline
                 capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_all.data_ptr()))
             else:
-                sset.d_all.zero_()
-                kev[i][0].record(stream)
-                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_local.data_ptr()))
-                kev[i][1].record(stream)
-                sset.d_all.index_copy_(0, sset.d_ids, sset.d_local[:1])
-                dist.all_reduce(sset.d_all, op=dist.ReduceOp.SUM)
+                sset.linearize_device()  # zero, kernel (records written in place), ONE all-reduce
             ev[i][1].record(stream)
         barrier()
         step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-        kern_ms = step_ms if world == 1 else np.array([a.elapsed_time(b) for a, b in kev])
         dev_total_ms = float(step_ms.sum())
         rec = sset.d_all.cpu().numpy()
         n_inliers = int(rec[rank, 121])
         launches_dev = sset.set.launch_count() - launches0
+        if world == 1:
+            kern_ms = step_ms
+        else:  # kernel-only timing for the roofline (same launches, no collective)
+            for i in range(K):
+                if not args.no_flush:
+                    flush.fill_(i & 0xFF)
+                sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
+                kev[i][0].record(stream)
+                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_local.data_ptr()))
+                kev[i][1].record(stream)
+            barrier()
+            kern_ms = np.array([a.elapsed_time(b) for a, b in kev])
 
         # ---- end-to-end arm: the public host entry point with HOST buffers (poses in, H/b records out) ----
         # N = 1: the C-ABI call itself (b2_factor_set_linearize), which is what NonlinearFactorSetGPU.linearize and the C++
@@ -291,6 +298,9 @@ def run_gpu(args):
             if not args.no_flush:
                 flush.fill_(i & 0xFF)
             torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             out = e2e_step(poses_c[W + i])
             e2e_s += time.perf_counter() - t0

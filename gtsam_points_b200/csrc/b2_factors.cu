@@ -35,6 +35,10 @@ namespace b2 {
 #define B2_THREADS 256
 #endif
 constexpr int kThreads = B2_THREADS;
+#ifndef B2_UNROLL
+#define B2_UNROLL 1
+#endif
+constexpr int kUnroll = B2_UNROLL;  // unroll of the software-pipelined VGICP loop (stage registers renamed instead of moved)
 constexpr int kPointsPerThread = 1;
 constexpr int kTile = kThreads * kPointsPerThread;
 constexpr int kAcc = 32;     // accumulator slots per partial record (29 used)
@@ -506,6 +510,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       StageGather cur = s2(b0);
       StageProbe nxt1 = b1;
       StageXYZ<PT> nxt2 = a2;
+#pragma unroll kUnroll
       for (uint32_t j = 0; j < J; j++) {
         const StageXYZ<PT> in0 = s0(j + 3);
         const StageProbe in1 = s1(nxt2);

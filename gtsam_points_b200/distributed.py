@@ -73,6 +73,9 @@ class ShardedFactorSet:
         self.d_local = torch.zeros((F, RECORD), dtype=torch.float64, device=self.device)
         self.d_all = torch.zeros((self.num_global, RECORD), dtype=torch.float64, device=self.device)
         self.d_ids = torch.as_tensor(self.global_ids, device=self.device)
+        # contiguous ownership (ids first..first+F_local-1): the kernel writes its records straight into the shared buffer
+        self.contiguous = len(self.global_ids) > 0 and bool(np.all(np.diff(self.global_ids) == 1))
+        self.first = int(self.global_ids[0]) if len(self.global_ids) else 0
         pin = self.device.type == "cuda"
         self.h_deltas = torch.zeros((F, 16), dtype=torch.float64, pin_memory=pin)
         self.h_all = torch.zeros((self.num_global, RECORD), dtype=torch.float64, pin_memory=pin)
@@ -83,11 +86,14 @@ class ShardedFactorSet:
         torch, dist = self.torch, self.dist
         self.d_all.zero_()
         if self.local_factors:
+            direct = self.compute is None and self.contiguous
+            dst = self.d_all[self.first : self.first + len(self.local_factors)] if direct else self.d_local
             if self.compute is None:
-                capi.check(capi.lib().b2_factor_set_linearize_device(self.set.h, self.d_deltas.data_ptr(), self.d_local.data_ptr()))
+                capi.check(capi.lib().b2_factor_set_linearize_device(self.set.h, self.d_deltas.data_ptr(), dst.data_ptr()))
             else:
                 self.d_local.copy_(torch.as_tensor(np.asarray(self.compute(self.d_deltas.cpu().numpy()))))
-            self.d_all.index_copy_(0, self.d_ids, self.d_local[: len(self.local_factors)])
+            if not direct:
+                self.d_all.index_copy_(0, self.d_ids, self.d_local[: len(self.local_factors)])
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.d_all, op=dist.ReduceOp.SUM, group=self.group)
         return self.d_all
