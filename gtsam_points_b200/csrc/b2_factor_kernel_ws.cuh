@@ -1,0 +1,592 @@
+// b2_factor_kernel_ws.cuh -- the hot kernel: warp-specialised fused correspondence search + linearization.
+// Included by b2_factors.cu after the shared pieces (FactorDesc, accumulate_point, warp_reduce32, epilogue).
+//
+// Why warp specialisation.  One correspondence is the dependent chain
+//     coordinates -> rotate/floor/hash -> bucket group -> voxel id -> voxel record + source covariance -> ~175 FP64 ops
+// and the reduction needs 29 float64 accumulators per thread (58 registers) plus the pose.  A single-role kernel
+// therefore runs at 8 warps / SM and cannot hide three dependent memory round trips (round-1 measurement: 53.7 us per
+// 1M points, FP64 pipe 24 % busy, 44 % of samples stalled on the scoreboard).  Here the CTA (one per SM, persistent)
+// is split with `setmaxnreg` into
+//   * kP PROBE warps with few registers: stream coordinates, rotate, floor, hash, probe the voxel table (or walk the
+//     kd-tree / re-read the frozen correspondence), store corr[], issue L2 prefetches for the voxel record and the
+//     covariance lines of every hit, and append the HITS ONLY -- compacted with a ballot -- as 32-byte items
+//     (R p, point index, target id) to a shared-memory ring;
+//   * kC ACCUMULATE warps with many registers: pop dense batches of 32 items, gather record + covariance (L2 hits
+//     thanks to the prefetch, issued one batch ahead of their use), do the float64 arithmetic, keep the accumulators
+//     in registers for the CTA's whole run of a factor.
+// Compaction removes the divergence waste of the fused form (38 % of the points of the bench workload have no voxel),
+// the probe chain is hidden by (kP / 4) independent warps per scheduler, and the FP64 pipe sees dense warps only.
+//
+// Determinism.  Every probe warp owns ONE ring (single producer, single consumer), tile -> probe warp assignment is
+// static, an accumulate warp drains its kP / kC rings in strict rotation in batches of exactly 32 consecutive items, and
+// all cross-warp / cross-CTA sums run in a fixed order: results are bit-reproducible run to run.
+// Liveness.  A probe warp blocks only when its own ring holds > cap - 32 items (then its consumer can pop a batch when
+// it reaches that ring) or at the end of a factor run until the consumer acknowledges; an accumulate warp waits on a ring
+// only while it holds < 32 items and is not finished, in which case its producer is not blocked.  Spins are bounded
+// (trap instead of hanging the GPU).
+#pragma once
+
+namespace b2 {
+namespace ws {
+
+#ifndef B2_WS_PRODUCERS
+#define B2_WS_PRODUCERS 8
+#endif
+#ifndef B2_WS_CONSUMERS
+#define B2_WS_CONSUMERS 8
+#endif
+#ifndef B2_WS_REGS_PRODUCER
+#define B2_WS_REGS_PRODUCER 88
+#endif
+#ifndef B2_WS_REGS_CONSUMER
+#define B2_WS_REGS_CONSUMER 168
+#endif
+#ifndef B2_WS_RING
+#define B2_WS_RING 256
+#endif
+#ifndef B2_WS_PPL
+#define B2_WS_PPL 2
+#endif
+#ifndef B2_WS_POSE_SMEM
+#define B2_WS_POSE_SMEM 0  // accumulate warps re-read the pose from shared memory instead of holding it in registers
+#endif
+#ifndef B2_WS_LOOKAHEAD
+#define B2_WS_LOOKAHEAD 0  // 1: accumulate warps issue the gathers of batch k+1 (into registers) before the arithmetic of batch k
+                           // 2: they prefetch batch k+1's operands into L1 instead (no registers held); 0: no lookahead
+#endif
+
+constexpr int kP = B2_WS_PRODUCERS;
+constexpr int kC = B2_WS_CONSUMERS;
+constexpr int kThreads = (kP + kC) * 32;
+constexpr int kPPL = B2_WS_PPL;             // points per probe lane and tile (independent chains interleaved for ILP)
+constexpr int kWarpPoints = 32 * kPPL;      // contiguous source points per probe warp and tile
+constexpr int kTile = kP * kWarpPoints;     // source points per CTA tile
+constexpr uint32_t kPrefetchAhead = 3;      // tiles between the L2 prefetch of a tile's coordinates and their use
+constexpr int kRing = B2_WS_RING;           // items per ring (power of two, >= 64)
+constexpr int kRingsPerConsumer = kP / kC;
+static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
+static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 64 + 2 * kWarpPoints, "ring capacity: a tile's hits + two batches of publication lag + one batch");
+static_assert(kWarpPoints * 4 % 128 == 0 || kPPL == 1, "coordinate prefetch works on whole lines");
+constexpr size_t kRingBytes = static_cast<size_t>(kP) * 2 * kRing * sizeof(double2);
+
+constexpr unsigned kSpinLimit = 1u << 22;  // polls (with sleeps: seconds) before a wait traps: a protocol bug must not hang the GPU
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v) : "memory");
+}
+// A waiting warp must not compete with the working warps of its scheduler for issue slots: sleep between polls.
+struct Backoff {
+  unsigned ns, max_ns, polls;
+  __device__ __forceinline__ explicit Backoff(unsigned first_ns, unsigned cap_ns) : ns(first_ns), max_ns(cap_ns), polls(0u) {}
+  __device__ __forceinline__ void wait() {
+    __nanosleep(ns);
+    if (ns < max_ns) ns *= 2u;
+    if (++polls > kSpinLimit) __trap();
+  }
+};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kC * 32) : "memory"); }
+
+#ifdef B2_WS_TIMING
+// development aid: per-CTA {start, probe warps done, accumulate warps done} timestamps of the last launch (ns)
+__device__ unsigned long long g_cta_times[1024 * 4];
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
+struct Shared {
+  FactorDesc desc;  // accumulate-side copy of the current factor's descriptor (flush / epilogue)
+  double red[kC][kAcc];
+  double tot[kAcc];
+  double A[36], X[36], D[36];
+  double R[9], t[3];  // pose the residuals of the current factor run are evaluated at (accumulate side)
+  double RL[9];       // rotation of its linearization point (== R when linearizing)
+  int flag;
+  // ring control words, one set per probe warp (all monotonic counters)
+  uint32_t tail[kP];  // items published by the probe warp
+  uint32_t head[kP];  // items taken by the accumulate warp
+  uint32_t done[kP];  // factor runs completed by the probe warp (tail is final for run e once done == e + 1)
+  uint32_t ack[kP];   // factor runs the accumulate warp has finished draining
+  double probe_pose[kP][12];  // per probe warp: R (9, row-major) | t (3) of the factor run it is working on
+};
+
+// tiles of CTA c: [c * T / G, (c + 1) * T / G) -- contiguous and balanced; the host uses the same formula for the slots
+__host__ __device__ __forceinline__ uint32_t cta_tile_begin(uint32_t c, uint32_t T, uint32_t G) {
+  return static_cast<uint32_t>(static_cast<unsigned long long>(c) * T / G);
+}
+
+// stride S ~ n / golden ratio with gcd(S, n) == 1: v -> (v * S) mod n is a permutation that spreads any run of v evenly
+inline uint32_t golden_stride(uint32_t n) {
+  if (n <= 2u) return 1u;
+  uint32_t s = static_cast<uint32_t>(static_cast<double>(n) * 0.6180339887498949);
+  if (s < 1u) s = 1u;
+  auto gcd = [](uint32_t a, uint32_t b) {
+    while (b) {
+      const uint32_t r = a % b;
+      a = b;
+      b = r;
+    }
+    return a;
+  };
+  while (gcd(s, n) != 1u) s++;
+  return s % n == 0u ? 1u : s % n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-factor flush by the accumulate warpgroup(s): warp butterfly -> cross-warp sum -> fixed slot; the last CTA of the
+// factor sums the slots in slot order and runs the epilogue (H_t = X^T A' X, ...).
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int ctid, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
+                                             const double* __restrict__ poses_lin) {
+  constexpr int kCT = kC * 32;
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const double w = warp_reduce32(v, lane);
+  sh.red[warp][lane] = w;
+  consumer_barrier();
+  const FactorDesc& d = sh.desc;
+  const uint32_t slot = blockIdx.x - d.cta_first[MODE];
+  if (warp == 0) {
+    double s = sh.red[0][lane];
+#pragma unroll
+    for (int k = 1; k < kC; k++) s += sh.red[k][lane];
+    partials[(static_cast<size_t>(d.slot_begin[MODE]) + slot) * kAcc + lane] = s;
+    __threadfence();  // only the writing warp pays for the fence
+  }
+  consumer_barrier();
+  if (ctid == 0) {
+    const unsigned int prev = atomicAdd(&counters[d.out_index], 1u);
+    sh.flag = (prev == d.num_slots[MODE] - 1u) ? 1 : 0;
+  }
+  consumer_barrier();
+  if (!sh.flag) return;
+
+  // ---- last CTA of this factor ----
+  __threadfence();
+  {
+    double s = 0.0;
+    for (uint32_t sl = warp; sl < d.num_slots[MODE]; sl += kC) s += __ldcg(&partials[(static_cast<size_t>(d.slot_begin[MODE]) + sl) * kAcc + lane]);
+    sh.red[warp][lane] = s;
+  }
+  consumer_barrier();
+  if (ctid < kAcc) {
+    double s = sh.red[0][ctid];
+#pragma unroll
+    for (int k = 1; k < kC; k++) s += sh.red[k][ctid];
+    sh.tot[ctid] = s;
+  }
+  if (ctid == 0) counters[d.out_index] = 0u;  // re-arm for the next launch
+  consumer_barrier();
+
+  if (MODE == MODE_ERROR) {
+    if (ctid == 0) {
+      out[d.out_index] = sh.tot[27];
+      __threadfence_system();  // `out` may be mapped host memory
+    }
+    consumer_barrier();
+    return;
+  }
+  epilogue_build(sh.A, sh.X, sh.D, sh.tot, sh.R, sh.t, ctid);
+  consumer_barrier();
+  double* rec = out + static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES;
+  epilogue_store(rec, sh.A, sh.X, sh.D, sh.tot, ctid);
+  if (ctid >= 100 && ctid < 116) {
+    // remember the linearization point with the factor (error-only launches of ANY set read it back)
+    d.lin_pose[ctid - 100] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (ctid - 100));
+  }
+  __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
+  consumer_barrier();
+  (void)kCT;
+}
+
+// One ring item as the accumulate warp holds it: what the probe warp sent (meta) + the gathered operands.
+struct Batch {
+  double u0, u1, u2;
+  uint32_t i;  // stored position of the source point
+  int id;      // target record
+  bool valid;
+  TargetRec T;
+  SourceCov A;
+};
+
+__device__ __forceinline__ void load_meta(Batch& b, const double2* __restrict__ ring, uint32_t head, uint32_t n, int lane) {
+  b.valid = static_cast<uint32_t>(lane) < n;
+  const uint32_t slot = (head + lane) & (kRing - 1);
+  const double2 q0 = ring[slot];
+  const double2 q1 = ring[kRing + slot];
+  b.u0 = q0.x;
+  b.u1 = q0.y;
+  b.u2 = q1.x;
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(q1.y));
+  // lanes beyond n read a stale slot: clamp to element 0 (always allocated), masked through `valid`
+  b.i = b.valid ? static_cast<uint32_t>(bits) : 0u;
+  b.id = b.valid ? static_cast<int>(bits >> 32) : 0;
+}
+
+template <typename CT>
+__device__ __forceinline__ void load_operands(Batch& b, const double* __restrict__ records, const CT* __restrict__ cv, size_t n_pad) {
+  b.T = load_record(records, b.id);
+  b.A = load_cov(cv, n_pad, b.i);
+}
+
+// Pull the operands of a batch into L1 (no registers held): the loads issued one batch later hit there.
+template <typename CT>
+__device__ __forceinline__ void prefetch_operands(const Batch& b, const double* __restrict__ records, const CT* __restrict__ cv, size_t n_pad) {
+  const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(b.id) * kRecordDoubles);
+  prefetch_l1(rec);
+  prefetch_l1(rec + 72);
+#pragma unroll
+  for (int k = 0; k < 6; k++) prefetch_l1(cv + k * n_pad + b.i);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename PT, typename CT, int KIND, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
+  __shared__ Shared sh;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double2* const rings = reinterpret_cast<double2*>(dyn_smem);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kP) {
+    sh.tail[tid] = 0u;
+    sh.head[tid] = 0u;
+    sh.done[tid] = 0u;
+    sh.ack[tid] = 0u;
+  }
+  __syncthreads();
+
+#ifdef B2_WS_TIMING
+  if (tid == 0) g_cta_times[blockIdx.x * 4 + 0] = globaltimer();
+#endif
+  const uint32_t G = gridDim.x;
+  const uint32_t tile_lo = cta_tile_begin(blockIdx.x, num_tiles, G);
+  const uint32_t tile_hi = cta_tile_begin(blockIdx.x + 1, num_tiles, G);
+
+  if (warp < kP) {
+    // ================================================= PROBE warps =================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_WS_REGS_PRODUCER));
+    const int p = warp;
+    double2* const ring = rings + static_cast<size_t>(p) * 2 * kRing;
+    uint32_t tail = 0u, run = 0u;
+    uint32_t tile = tile_lo;
+    while (tile < tile_hi) {
+      const FactorDesc* __restrict__ dg = descs + __ldg(tile_factor + tile);
+      const uint32_t n = dg->n;
+      const size_t n_pad = dg->n_pad;
+      const uint32_t f_tile_begin = dg->tile_begin;
+      const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
+      const uint32_t out_index = dg->out_index;
+      const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
+      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
+      const double* __restrict__ records = dg->records;
+      int32_t* __restrict__ corr = dg->corr;
+      const VoxelBucket* __restrict__ buckets = dg->buckets;
+      const uint32_t bucket_mask = dg->bucket_mask;
+      const double inv_leaf = dg->inv_leaf;
+      // Residuals / correspondences are evaluated at this pose (linearize: the linearization point itself).  It lives in
+      // this warp's shared-memory slot, not in registers: 24 registers less per probe thread, re-read (broadcast) per tile.
+      __syncwarp();
+      if (lane < 12) {
+        const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(out_index) * 16;
+        sh.probe_pose[p][lane] = __ldg(pe + (lane < 9 ? (lane / 3) * 4 + lane % 3 : (lane - 9) * 4 + 3));
+      }
+      __syncwarp();
+      const double(&R)[9] = *reinterpret_cast<const double(*)[9]>(&sh.probe_pose[p][0]);
+      const double(&t)[3] = *reinterpret_cast<const double(*)[3]>(&sh.probe_pose[p][9]);
+      const KdTreeView tv{dg->nodes, dg->leaf_pts, dg->leaf_pts + dg->leaf_n_pad, dg->leaf_pts + 2 * static_cast<size_t>(dg->leaf_n_pad)};
+      const double max_sq = dg->max_sq;
+
+      // Virtual tile v of the factor (the CTA owns a contiguous range of them) is physical tile (v * S) mod n_tiles with
+      // S ~ 0.618 n_tiles coprime to n_tiles: every CTA samples the cloud quasi-uniformly, so dense and empty regions of the
+      // (Morton-ordered) cloud spread evenly over the SMs instead of landing on a few of them.
+      const uint32_t f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
+      auto phys_tile = [&](uint32_t vt) { return static_cast<uint32_t>(static_cast<unsigned long long>(vt - f_tile_begin) * perm_stride % f_num_tiles); };
+      auto next_tile = [&](uint32_t pt) {  // physical tile of v + 1 given that of v
+        pt += perm_stride;
+        return pt >= f_num_tiles ? pt - f_num_tiles : pt;
+      };
+      // The coordinate stream (and, in error mode, the frozen correspondences) of a tile is pulled into L2 kPrefetchAhead
+      // tiles before its use: one prefetch instruction per tile, no registers or scoreboard slots held across iterations.
+      constexpr uint32_t kLinesPerPlane = kWarpPoints * sizeof(PT) / 128;  // 128-byte lines of one coordinate plane per warp tile
+      auto prefetch_tile = [&](uint32_t pt) {
+        const uint32_t base = pt * kTile + p * kWarpPoints;
+        if (base >= n) return;
+        const uint32_t first = base + (lane % kLinesPerPlane) * (128 / sizeof(PT));  // first element of this lane's line
+        if (lane < 3 * kLinesPerPlane && first < n_pad) prefetch_l2(px + (lane / kLinesPerPlane) * n_pad + first);
+        if (MODE == MODE_ERROR && lane >= 24 && lane < 24 + kWarpPoints / 32 && base + (lane - 24) * 32 < n_pad) prefetch_l2(corr + base + (lane - 24) * 32);
+      };
+      uint32_t pt_cur = phys_tile(tile), pt_ahead = pt_cur;
+      for (uint32_t k = 0; k < kPrefetchAhead; k++) {
+        if (tile + k < run_end) prefetch_tile(pt_ahead);
+        pt_ahead = next_tile(pt_ahead);
+      }
+
+#pragma unroll 1
+      for (; tile < run_end; tile++, pt_cur = next_tile(pt_cur), pt_ahead = next_tile(pt_ahead)) {
+        if (tile + kPrefetchAhead < run_end) prefetch_tile(pt_ahead);
+        const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
+        // kPPL independent points per lane: their dependent chains (rotate -> floor -> hash -> bucket group -> match) interleave
+        double u[kPPL][3];
+        int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
+        uint32_t grp_idx[kPPL];
+        bool ok[kPPL];
+        BucketGroup grp[kPPL];
+        {
+          PT x[kPPL], y[kPPL], z[kPPL];
+#pragma unroll
+          for (int k = 0; k < kPPL; k++) {
+            const uint32_t i = base + k * 32;
+            ok[k] = i < n;
+            const uint32_t j = ok[k] ? i : 0u;  // out-of-range lanes read element 0 (always allocated) and are masked through ok
+            x[k] = __ldg(px + j);
+            y[k] = __ldg(px + n_pad + j);
+            z[k] = __ldg(px + 2 * n_pad + j);
+            id[k] = -1;
+            if (MODE == MODE_ERROR) id[k] = ok[k] ? __ldg(corr + j) : -1;
+          }
+#pragma unroll
+          for (int k = 0; k < kPPL; k++) {
+            rotate_point(R, static_cast<double>(x[k]), static_cast<double>(y[k]), static_cast<double>(z[k]), u[k][0], u[k][1], u[k][2]);
+            if (MODE == MODE_LINEARIZE && KIND == 0) {
+              cx[k] = voxel_coord1(__dadd_rn(u[k][0], t[0]), inv_leaf);
+              cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
+              cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
+              grp_idx[k] = voxel_hash(cx[k], cy[k], cz[k]) & bucket_mask;
+              grp[k] = load_group(buckets, grp_idx[k]);
+            }
+          }
+        }
+        uint32_t mask[kPPL], cnt = 0u;
+#pragma unroll
+        for (int k = 0; k < kPPL; k++) {
+          if (MODE == MODE_LINEARIZE) {
+            if (KIND == 0) {
+              id[k] = match_group(grp[k], cx[k], cy[k], cz[k]);
+              uint32_t g = grp_idx[k];
+              while (id[k] == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
+                g = (g + 1) & bucket_mask;
+                id[k] = match_group(load_group(buckets, g), cx[k], cy[k], cz[k]);
+              }
+            } else {
+              double sq;
+              id[k] = ok[k] ? kdtree_nn1(tv, __dadd_rn(u[k][0], t[0]), __dadd_rn(u[k][1], t[1]), __dadd_rn(u[k][2], t[2]), max_sq, &sq) : -1;
+            }
+            if (ok[k]) corr[base + k * 32] = id[k];
+          }
+          mask[k] = __ballot_sync(0xffffffffu, ok[k] && id[k] >= 0);
+          cnt += __popc(mask[k]);
+        }
+        if (cnt == 0u) continue;
+        // wait for room in the ring
+        if (tail + cnt - ld_acquire(&sh.head[p]) > static_cast<uint32_t>(kRing)) {
+          Backoff bo(64u, 256u);
+          do bo.wait();
+          while (tail + cnt - ld_acquire(&sh.head[p]) > static_cast<uint32_t>(kRing));
+        }
+#pragma unroll
+        for (int k = 0; k < kPPL; k++) {
+          if ((mask[k] >> lane) & 1u) {
+            const uint32_t slot = (tail + __popc(mask[k] & ((1u << lane) - 1u))) & (kRing - 1);
+            const unsigned long long bits = static_cast<unsigned long long>(base + k * 32) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[k])) << 32);
+            ring[slot] = make_double2(u[k][0], u[k][1]);
+            ring[kRing + slot] = make_double2(u[k][2], __longlong_as_double(static_cast<long long>(bits)));
+            // the accumulate warp will gather these: start them towards L2 now
+            const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(id[k]) * kRecordDoubles);
+            prefetch_l2(rec);
+            prefetch_l2(rec + 72);
+          }
+          if (lane < 12) {
+            // covariance lines of this 32-point group: 6 planes x 2 halves of 16 points
+            const uint32_t half = lane & 1, plane = lane >> 1;
+            if ((mask[k] >> (16 * half)) & 0xffffu) prefetch_l2(cv + plane * n_pad + (base - lane) + k * 32 + 16 * half);
+          }
+          tail += __popc(mask[k]);
+        }
+        __syncwarp();
+        if (lane == 0) st_release(&sh.tail[p], tail);
+      }
+      // end of this CTA's run of the factor: publish, then wait until the accumulate warp has drained the ring
+      run++;
+      __syncwarp();
+      if (lane == 0) st_release(&sh.done[p], run);
+      {
+        Backoff bo(128u, 512u);
+        while (ld_acquire(&sh.ack[p]) != run) bo.wait();
+      }
+    }
+#ifdef B2_WS_TIMING
+    if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 1], globaltimer());
+#endif
+  } else {
+    // =============================================== ACCUMULATE warps ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_WS_REGS_CONSUMER));
+    const int cw = warp - kP;          // accumulate warp index
+    const int ctid = tid - kP * 32;    // thread index within the accumulate group
+    uint32_t head[kRingsPerConsumer], head_pub[kRingsPerConsumer];  // items taken / items handed back to the probe warp
+#pragma unroll
+    for (int r = 0; r < kRingsPerConsumer; r++) head[r] = head_pub[r] = 0u;
+    uint32_t run = 0u;
+    uint32_t tile = tile_lo;
+    double acc[kAcc];
+    while (tile < tile_hi) {
+      const uint32_t f = __ldg(tile_factor + tile);
+      consumer_barrier();  // previous flush is done with sh.desc
+      if (ctid < static_cast<int>(sizeof(FactorDesc) / 4)) reinterpret_cast<uint32_t*>(&sh.desc)[ctid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + ctid);
+      consumer_barrier();
+      const FactorDesc& d = sh.desc;
+      if (ctid < 21) {
+        const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16;
+        const double* pl = (MODE == MODE_ERROR) ? d.lin_pose : pe;
+        if (ctid < 9)
+          sh.R[ctid] = __ldg(pe + (ctid / 3) * 4 + ctid % 3);
+        else if (ctid < 12)
+          sh.t[ctid - 9] = __ldg(pe + (ctid - 9) * 4 + 3);
+        else
+          sh.RL[ctid - 12] = __ldg(pl + ((ctid - 12) / 3) * 4 + (ctid - 12) % 3);
+      }
+      consumer_barrier();
+#if B2_WS_POSE_SMEM
+      // the pose stays in shared memory and is re-read (broadcast) by each batch: 24 registers less per accumulate thread
+      const double(&RL)[9] = sh.RL;
+      const double(&t)[3] = sh.t;
+#else
+      double RL[9], t[3];
+#pragma unroll
+      for (int k = 0; k < 9; k++) RL[k] = sh.RL[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) t[k] = sh.t[k];
+#endif
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
+      const double* __restrict__ records = d.records;
+      const CT* __restrict__ cv = static_cast<const CT*>(d.covs);
+      const size_t n_pad = d.n_pad;
+      const uint32_t run_end = min(tile_hi, d.tile_begin + d.num_tiles);
+      run++;
+
+      // Strict rotation over this warp's rings, in batches of 32 consecutive items.  The gathers of a batch are issued one
+      // batch ahead of its arithmetic (two register buffers in ping-pong; availability changes timing only, never order).
+      uint32_t finished = 0u;
+      int r = 0;
+      constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
+      // Takes the next batch in rotation into `dst`.  blocking: wait for it; otherwise give up if it is not there yet.
+      // Returns false when nothing was taken (not ready, or every ring of this run is finished).
+      auto acquire = [&](Batch& dst, bool blocking) -> bool {
+        while (finished != kAllFinished) {
+          while (finished & (1u << r)) r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+          const int p = cw + r * kC;
+          uint32_t hd = 0u, hd_pub = 0u;
+#pragma unroll
+          for (int k = 0; k < kRingsPerConsumer; k++)
+            if (k == r) hd = head[k], hd_pub = head_pub[k];
+          // Hand slots back lazily: everything up to the START of the most recent batch taken from this ring has been through
+          // its arithmetic by now (its shared-memory reads completed long ago), so no fence is needed in this loop.
+          if (lane == 0) st_volatile(&sh.head[p], hd_pub);
+          uint32_t nb = 0u;
+          bool fin = false;
+          Backoff bo(32u, 64u);
+          while (true) {
+            const uint32_t dn = ld_acquire(&sh.done[p]);
+            const uint32_t tl = ld_acquire(&sh.tail[p]);
+            const uint32_t avail = tl - hd;
+            if (avail >= 32u) {
+              nb = 32u;
+              break;
+            }
+            if (dn == run) {  // the probe warp finished this run: `tl` is final
+              nb = avail;
+              fin = true;
+              break;
+            }
+            if (!blocking) return false;
+            bo.wait();
+          }
+          if (nb > 0u) {
+            load_meta(dst, rings + static_cast<size_t>(p) * 2 * kRing, hd, nb, lane);
+#if B2_WS_LOOKAHEAD == 2
+            prefetch_operands<CT>(dst, records, cv, n_pad);
+#else
+            load_operands<CT>(dst, records, cv, n_pad);
+#endif
+#pragma unroll
+            for (int k = 0; k < kRingsPerConsumer; k++)
+              if (k == r) head_pub[k] = hd, head[k] = hd + nb;
+            hd += nb;
+          }
+          if (fin) {
+            finished |= 1u << r;
+            // the ring is drained for this run: release the probe warp (after the slot reads above: fence + store)
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kRingsPerConsumer; k++)
+              if (k == r) head_pub[k] = hd;
+            if (lane == 0) {
+              st_volatile(&sh.head[p], hd);
+              st_release(&sh.ack[p], run);
+            }
+          }
+          r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+          if (nb > 0u) return true;
+        }
+        return false;
+      };
+      auto accumulate = [&](Batch& b) {
+#if B2_WS_LOOKAHEAD == 2
+        load_operands<CT>(b, records, cv, n_pad);  // prefetched into L1 one batch ago
+#endif
+        if (b.valid) accumulate_point<MODE>(acc, RL, t, b.u0, b.u1, b.u2, b.T, b.A);
+      };
+#if B2_WS_LOOKAHEAD
+      Batch bufA, bufB;
+      bool haveA = false;
+      while (true) {
+        const bool gotB = acquire(bufB, !haveA);
+        if (haveA) accumulate(bufA);
+        if (!gotB) {
+          if (!haveA && finished == kAllFinished) break;
+          haveA = false;
+          continue;
+        }
+        haveA = acquire(bufA, false);
+        accumulate(bufB);
+      }
+#else
+      {
+        Batch buf;
+        while (acquire(buf, true)) accumulate(buf);
+      }
+#endif
+#ifdef B2_WS_TIMING
+      if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 2], globaltimer());
+      if (lane == 0) atomicMin(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());
+#endif
+      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, poses_lin);
+      tile = run_end;
+    }
+  }
+}
+
+}  // namespace ws
+}  // namespace b2

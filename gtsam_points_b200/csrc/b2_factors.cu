@@ -15,12 +15,15 @@
 //     J' = [-hat(R p) | I]; since J_target = J' X and J_source = -J' D with X = [[I,0],[-hat(t),I]], D = diag(R,R),
 //     the five reference blocks are recovered once per factor: H_t = X^T A' X, H_s = D^T A' D, H_ts = -X^T A' D,
 //     b_t = X^T c', b_s = -D^T c'.  (~170 DFMA-class instructions per correspondence instead of ~1000.)
-//   * accumulators live in registers across a CTA's whole tile sequence; one transposing butterfly reduction
-//     (31 shuffles for 32 values) per CTA and factor; partial sums go to fixed slots and the last CTA of a factor
-//     reduces the slots in slot order => results are bit-reproducible run to run.
-//   * all factors of a set are covered by one launch: the grid walks a tile list (tile -> factor), CTA c takes tiles
-//     c, c+G, c+2G, ... so work is balanced and every CTA meets each factor in one contiguous run.
+//   * the kernel (b2_factor_kernel_ws.cuh) is warp-specialised: probe warps search correspondences and feed the hits,
+//     compacted, through shared-memory rings to accumulate warps that own the float64 accumulators.
+//   * one transposing butterfly reduction (31 shuffles for 32 values) per CTA and factor; partial sums go to fixed
+//     slots and the last CTA of a factor reduces the slots in slot order => results are bit-reproducible run to run.
+//   * all factors of a set are covered by one launch: the grid walks a tile list (tile -> factor), CTA c takes the
+//     contiguous, balanced tile range [c T / G, (c + 1) T / G), so a CTA meets few factors and each in one run.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -31,21 +34,7 @@
 
 namespace b2 {
 
-#ifndef B2_THREADS
-#define B2_THREADS 256
-#endif
-constexpr int kThreads = B2_THREADS;
-#ifndef B2_UNROLL
-#define B2_UNROLL 1
-#endif
-constexpr int kUnroll = B2_UNROLL;  // unroll of the software-pipelined VGICP loop (stage registers renamed instead of moved)
-constexpr int kPointsPerThread = 1;
-constexpr int kTile = kThreads * kPointsPerThread;
-constexpr int kAcc = 32;     // accumulator slots per partial record (29 used)
-#ifndef B2_MINBLOCKS
-#define B2_MINBLOCKS 1
-#endif
-constexpr int kMinBlocksPerSM = B2_MINBLOCKS;
+constexpr int kAcc = 32;  // accumulator slots per partial record (29 used)
 
 enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
 
@@ -74,7 +63,8 @@ struct FactorDesc {
   uint32_t slot_begin[2];  // per mode
   uint32_t num_slots[2];   // per mode
   uint32_t out_index;      // index of the factor in its set (pose / result / counter)
-  uint32_t pad2;
+  uint32_t cta_first[2];   // per mode: first CTA whose (contiguous) tile range touches this factor; slot = blockIdx.x - cta_first
+  uint32_t perm_stride;    // virtual -> physical tile permutation within the factor: (v * perm_stride) mod num_tiles
 };
 
 __device__ __forceinline__ double ldv(const float* p, size_t i) { return static_cast<double>(__ldg(p + i)); }
@@ -111,120 +101,54 @@ __device__ __forceinline__ int sym_idx(int i, int j) {
 }
 
 // accumulator layout: 0..5 A_rr (upper), 6..14 A_rt (row-major, rows = rotation), 15..20 A_tt (upper), 21..23 c_r, 24..26 c_t, 27 error, 28 count
-struct Shared {
-  FactorDesc desc;
-  double red[kThreads / 32][kAcc];
-  double tot[kAcc];
-  double A[36], X[36], D[36];
-  double R[9], t[3];
-  int flag;
-};
 
-template <int MODE>
-__device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], const double (&Rr)[9], const double (&tr)[3], double* __restrict__ partials,
-                                             unsigned int* __restrict__ counters, double* __restrict__ out, uint32_t G, const double* __restrict__ poses_lin) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double w = warp_reduce32(v, lane);
-  sh.red[warp][lane] = w;
-  if (tid == 0) {
-    // the pose lives in registers (static indices only); the epilogue indexes it dynamically, so stage it in shared memory
-#pragma unroll
-    for (int k = 0; k < 9; k++) sh.R[k] = Rr[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) sh.t[k] = tr[k];
+// Per-factor epilogue, step 1 (threads 0..35): unpack A' (symmetric 6x6, tangent order [rot, trans]) from the reduced
+// accumulators and build X = [[I, 0], [-hat(t), I]] and D = diag(R, R).
+__device__ __forceinline__ void epilogue_build(double* __restrict__ A, double* __restrict__ X, double* __restrict__ D, const double* __restrict__ tot,
+                                               const double* __restrict__ R, const double* __restrict__ t, int tid) {
+  if (tid >= 36) return;
+  const int i = tid / 6, j = tid % 6;
+  double a;
+  if (i < 3 && j < 3)
+    a = tot[sym_idx(i, j)];
+  else if (i < 3)
+    a = tot[6 + i * 3 + (j - 3)];
+  else if (j < 3)
+    a = tot[6 + j * 3 + (i - 3)];
+  else
+    a = tot[15 + sym_idx(i - 3, j - 3)];
+  A[tid] = a;
+  double x = (i == j) ? 1.0 : 0.0;
+  if (i >= 3 && j < 3) {
+    const int r = i - 3, cc = j;
+    // -hat(t) = [[0, t2, -t1], [-t2, 0, t0], [t1, -t0, 0]]
+    if (r == 0 && cc == 1) x = t[2];
+    if (r == 0 && cc == 2) x = -t[1];
+    if (r == 1 && cc == 0) x = -t[2];
+    if (r == 1 && cc == 2) x = t[0];
+    if (r == 2 && cc == 0) x = t[1];
+    if (r == 2 && cc == 1) x = -t[0];
   }
-  const double* R = sh.R;
-  const double* t = sh.t;
-  __syncthreads();
-  const FactorDesc& d = sh.desc;
-  const uint32_t c = blockIdx.x;
-  const uint32_t slot = (c + G - (d.tile_begin % G)) % G;
-  if (warp == 0) {
-    double s = sh.red[0][lane];
-#pragma unroll
-    for (int k = 1; k < kThreads / 32; k++) s += sh.red[k][lane];
-    partials[(static_cast<size_t>(d.slot_begin[MODE]) + slot) * kAcc + lane] = s;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(&counters[d.out_index], 1u);
-    sh.flag = (prev == d.num_slots[MODE] - 1u) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!sh.flag) return;
+  X[tid] = x;
+  D[tid] = ((i < 3) == (j < 3)) ? R[(i % 3) * 3 + (j % 3)] : 0.0;
+}
 
-  // ---- last CTA of this factor: ordered reduction over the slots, then the per-factor epilogue ----
-  __threadfence();
-  {
-    const int k = lane, part = warp;
-    double s = 0.0;
-    for (uint32_t sl = part; sl < d.num_slots[MODE]; sl += kThreads / 32) s += __ldcg(&partials[(static_cast<size_t>(d.slot_begin[MODE]) + sl) * kAcc + k]);
-    sh.red[part][k] = s;
-  }
-  __syncthreads();
-  if (tid < kAcc) {
-    double s = sh.red[0][tid];
-#pragma unroll
-    for (int k = 1; k < kThreads / 32; k++) s += sh.red[k][tid];
-    sh.tot[tid] = s;
-  }
-  if (tid == 0) counters[d.out_index] = 0u;  // re-arm for the next launch
-  __syncthreads();
-
-  if (MODE == MODE_ERROR) {
-    if (tid == 0) {
-      out[d.out_index] = sh.tot[27];
-      __threadfence_system();  // `out` may be mapped host memory
-    }
-    __syncthreads();
-    return;
-  }
-
-  double* rec = out + static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES;
-  if (tid < 36) {
-    const int i = tid / 6, j = tid % 6;
-    // A' (symmetric 6x6), tangent order [rot, trans]
-    double a;
-    if (i < 3 && j < 3)
-      a = sh.tot[sym_idx(i, j)];
-    else if (i < 3)
-      a = sh.tot[6 + i * 3 + (j - 3)];
-    else if (j < 3)
-      a = sh.tot[6 + j * 3 + (i - 3)];
-    else
-      a = sh.tot[15 + sym_idx(i - 3, j - 3)];
-    sh.A[tid] = a;
-    // X = [[I, 0], [-hat(t), I]]
-    double x = (i == j) ? 1.0 : 0.0;
-    if (i >= 3 && j < 3) {
-      const int r = i - 3, cc = j;
-      // -hat(t) = [[0, t2, -t1], [-t2, 0, t0], [t1, -t0, 0]]
-      if (r == 0 && cc == 1) x = t[2];
-      if (r == 0 && cc == 2) x = -t[1];
-      if (r == 1 && cc == 0) x = -t[2];
-      if (r == 1 && cc == 2) x = t[0];
-      if (r == 2 && cc == 0) x = t[1];
-      if (r == 2 && cc == 1) x = -t[0];
-    }
-    sh.X[tid] = x;
-    // D = diag(R, R)
-    sh.D[tid] = ((i < 3) == (j < 3)) ? R[(i % 3) * 3 + (j % 3)] : 0.0;
-  }
-  __syncthreads();
+// Step 2 (after a barrier): H_t = X^T A' X, H_s = D^T A' D, H_ts = -X^T A' D (threads 0..35), b_t = X^T c', b_s = -D^T c'
+// (threads 64..69), error / inlier count / padding (thread 96) -> the factor's b2_linearized record.
+__device__ __forceinline__ void epilogue_store(double* __restrict__ rec, const double* __restrict__ A, const double* __restrict__ X,
+                                               const double* __restrict__ D, const double* __restrict__ tot, int tid) {
   if (tid < 36) {
     const int i = tid / 6, j = tid % 6;
     double ht = 0.0, hs = 0.0, hts = 0.0;
     for (int a = 0; a < 6; a++) {
-      double xa = 0.0, da = 0.0, xd = 0.0;  // (A X)[a][j], (A D)[a][j]
+      double xa = 0.0, da = 0.0;  // (A X)[a][j], (A D)[a][j]
       for (int b = 0; b < 6; b++) {
-        xa += sh.A[a * 6 + b] * sh.X[b * 6 + j];
-        da += sh.A[a * 6 + b] * sh.D[b * 6 + j];
+        xa += A[a * 6 + b] * X[b * 6 + j];
+        da += A[a * 6 + b] * D[b * 6 + j];
       }
-      xd = da;
-      ht += sh.X[a * 6 + i] * xa;
-      hs += sh.D[a * 6 + i] * da;
-      hts -= sh.X[a * 6 + i] * xd;
+      ht += X[a * 6 + i] * xa;
+      hs += D[a * 6 + i] * da;
+      hts -= X[a * 6 + i] * da;
     }
     rec[tid] = ht;
     rec[36 + tid] = hs;
@@ -233,23 +157,18 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], cons
     const int i = tid - 64;
     double bt = 0.0, bs = 0.0;
     for (int a = 0; a < 6; a++) {
-      const double ca = sh.tot[21 + a];
-      bt += sh.X[a * 6 + i] * ca;
-      bs -= sh.D[a * 6 + i] * ca;
+      const double ca = tot[21 + a];
+      bt += X[a * 6 + i] * ca;
+      bs -= D[a * 6 + i] * ca;
     }
     rec[108 + i] = bt;
     rec[114 + i] = bs;
-  } else if (tid >= 128 && tid < 144) {
-    // remember the linearization point with the factor (error-only launches of ANY set read it back)
-    d.lin_pose[tid - 128] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (tid - 128));
   } else if (tid == 96) {
-    rec[120] = sh.tot[27];
-    rec[121] = sh.tot[28];
+    rec[120] = tot[27];
+    rec[121] = tot[28];
 #pragma unroll
     for (int k = 122; k < B2_LINEARIZED_DOUBLES; k++) rec[k] = 0.0;
   }
-  __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -364,8 +283,6 @@ __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const doub
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
 __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, double y, double z, double& u0, double& u1, double& u2) {
   u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
@@ -373,187 +290,11 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
   u2 = __dadd_rn(__dadd_rn(__dmul_rn(R[6], x), __dmul_rn(R[7], y)), __dmul_rn(R[8], z));
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// The fused kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
-//
-// A CTA takes tiles c, c+G, c+2G, ... (G = grid size); tiles of one factor are contiguous, so the CTA meets a factor
-// in one run of J tiles, thread `tid` owning element `tid` of each.  For VGICP the run is SOFTWARE-PIPELINED in
-// registers: a correspondence is the dependent chain  coordinates -> bucket group -> voxel record -> arithmetic, and the
-// 29 float64 accumulators leave room for only 8 warps per SM, so instead of hiding the chain behind other warps every
-// thread keeps the loads of its next three points in flight while it does the arithmetic of the current one:
-//     iteration j:  S0(j+3) issue coordinate loads        S1(j+2) rotate, floor, hash, issue bucket-group loads
-//                   S2(j+1) match -> voxel id, issue record + covariance loads        S3(j) arithmetic
-// ---------------------------------------------------------------------------------------------------------------
-template <typename PT>
-struct StageXYZ {  // S0 result: coordinates in flight
-  PT x, y, z;
-  uint32_t i;
-  int id;  // error mode: correspondence frozen at the last linearize (loaded with the coordinates); -1 when out of range
-};
-struct StageProbe {  // S1 result: bucket group in flight
-  double u0, u1, u2;
-  int cx, cy, cz;
-  uint32_t g;
-  uint32_t i;
-  int id;
-  BucketGroup grp;
-};
-struct StageGather {  // S2 result: target record + source covariance in flight
-  double u0, u1, u2;
-  int id;
-  TargetRec T;
-  SourceCov A;
-};
+}  // namespace b2
 
-template <typename PT, typename CT, int KIND, int MODE>
-__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM)
-factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
-              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
-  __shared__ Shared sh;
-  const int tid = threadIdx.x;
-  const uint32_t G = gridDim.x;
+#include "b2_factor_kernel_ws.cuh"
 
-  double acc[kAcc];
-  // pose at which residuals / Jacobians are evaluated (R, t) and rotation of the linearization point (Rl) for the fused covariance
-  double R[9], t[3], Rl_[9];
-
-  uint32_t tile = blockIdx.x;
-  while (tile < num_tiles) {
-    const int f = static_cast<int>(__ldg(tile_factor + tile));
-    __syncthreads();
-    if (tid < static_cast<int>(sizeof(FactorDesc) / 4)) {
-      reinterpret_cast<uint32_t*>(&sh.desc)[tid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + tid);
-    }
-    __syncthreads();
-    const FactorDesc& d = sh.desc;
-    {
-      const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16;
-      const double* pl = (MODE == MODE_ERROR) ? d.lin_pose : poses_lin + static_cast<size_t>(d.out_index) * 16;
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          R[r * 3 + c] = __ldg(pe + r * 4 + c);
-          Rl_[r * 3 + c] = __ldg(pl + r * 4 + c);
-        }
-        t[r] = __ldg(pe + r * 4 + 3);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
-
-    const uint32_t n = d.n;
-    const size_t n_pad = d.n_pad;
-    const PT* __restrict__ px = static_cast<const PT*>(d.pts);
-    const CT* __restrict__ cv = static_cast<const CT*>(d.covs);
-    const uint32_t tile_end = d.tile_begin + d.num_tiles;
-    const uint32_t J = (tile_end - tile + G - 1) / G;  // tiles of this factor owned by this CTA
-    const uint32_t base0 = (tile - d.tile_begin) * kTile + tid;
-    const uint32_t stride = G * kTile;
-    const double(&RL)[9] = (MODE == MODE_ERROR) ? Rl_ : R;
-
-#ifndef B2_VGICP_SIMPLE
-    if (KIND == 0) {
-      // ------------------------------------------- VGICP: register software pipeline -------------------------------------------
-      auto s0 = [&](uint32_t j) {
-        StageXYZ<PT> a;
-        const uint32_t i = base0 + j * stride;
-        const bool ok = j < J && i < n;
-        a.i = ok ? i : 0u;  // out-of-range lanes read element 0 (always allocated) and are masked through id = -1
-        a.x = __ldg(px + a.i);
-        a.y = __ldg(px + n_pad + a.i);
-        a.z = __ldg(px + 2 * n_pad + a.i);
-        a.id = ok ? 0 : -1;
-        if (MODE == MODE_ERROR) a.id = ok ? __ldg(d.corr + a.i) : -1;
-        return a;
-      };
-      auto s1 = [&](const StageXYZ<PT>& a) {
-        StageProbe b;
-        rotate_point(R, static_cast<double>(a.x), static_cast<double>(a.y), static_cast<double>(a.z), b.u0, b.u1, b.u2);
-        b.i = a.i;
-        b.id = a.id;
-        if (MODE == MODE_LINEARIZE) {
-          b.cx = voxel_coord1(__dadd_rn(b.u0, t[0]), d.inv_leaf);
-          b.cy = voxel_coord1(__dadd_rn(b.u1, t[1]), d.inv_leaf);
-          b.cz = voxel_coord1(__dadd_rn(b.u2, t[2]), d.inv_leaf);
-          b.g = voxel_hash(b.cx, b.cy, b.cz) & d.bucket_mask;
-          b.grp = load_group(d.buckets, b.g);
-        }
-        return b;
-      };
-      auto s2 = [&](const StageProbe& b) {
-        StageGather c;
-        c.u0 = b.u0;
-        c.u1 = b.u1;
-        c.u2 = b.u2;
-        c.id = b.id;
-        if (MODE == MODE_LINEARIZE) {
-          int r = match_group(b.grp, b.cx, b.cy, b.cz);
-          uint32_t g = b.g;
-          while (r == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
-            g = (g + 1) & d.bucket_mask;
-            r = match_group(load_group(d.buckets, g), b.cx, b.cy, b.cz);
-          }
-          if (b.id >= 0) {
-            c.id = r;
-            d.corr[b.i] = r;
-          }
-        }
-        c.T = load_record(d.records, c.id);
-        c.A = load_cov(cv, n_pad, b.i);
-        return c;
-      };
-
-      // prologue: fill the pipeline
-      StageXYZ<PT> a0 = s0(0), a1 = s0(1), a2 = s0(2);
-      StageProbe b0 = s1(a0), b1 = s1(a1);
-      StageGather cur = s2(b0);
-      StageProbe nxt1 = b1;
-      StageXYZ<PT> nxt2 = a2;
-#pragma unroll kUnroll
-      for (uint32_t j = 0; j < J; j++) {
-        const StageXYZ<PT> in0 = s0(j + 3);
-        const StageProbe in1 = s1(nxt2);
-        const StageGather in2 = s2(nxt1);
-        if (cur.id >= 0) accumulate_point<MODE>(acc, RL, t, cur.u0, cur.u1, cur.u2, cur.T, cur.A);
-        cur = in2;
-        nxt1 = in1;
-        nxt2 = in0;
-      }
-    } else
-#endif
-    {
-      // ------------------------------------------- GICP: kd-tree 1-NN per point -------------------------------------------
-      const KdTreeView tv{d.nodes, d.leaf_pts, d.leaf_pts + d.leaf_n_pad, d.leaf_pts + 2 * static_cast<size_t>(d.leaf_n_pad)};
-      for (uint32_t j = 0; j < J; j++) {
-        const uint32_t i = base0 + j * stride;
-        if (i >= n) continue;
-        double u0, u1, u2;
-        rotate_point(R, ldv(px, i), ldv(px + n_pad, i), ldv(px + 2 * n_pad, i), u0, u1, u2);
-        int id;
-        if (MODE == MODE_LINEARIZE) {
-          if (KIND == 0) {
-            id = lookup_voxel(d.buckets, d.bucket_mask, voxel_coord1(__dadd_rn(u0, t[0]), d.inv_leaf), voxel_coord1(__dadd_rn(u1, t[1]), d.inv_leaf),
-                              voxel_coord1(__dadd_rn(u2, t[2]), d.inv_leaf));
-          } else {
-            double sq;
-            id = kdtree_nn1(tv, __dadd_rn(u0, t[0]), __dadd_rn(u1, t[1]), __dadd_rn(u2, t[2]), d.max_sq, &sq);
-          }
-          d.corr[i] = id;
-        } else {
-          id = __ldg(d.corr + i);
-        }
-        if (id < 0) continue;
-        const TargetRec T = load_record(d.records, id);
-        const SourceCov A = load_cov(cv, n_pad, i);
-        accumulate_point<MODE>(acc, RL, t, u0, u1, u2, T, A);
-      }
-    }
-
-    flush_factor<MODE>(sh, acc, R, t, partials, counters, out, G, poses_lin);
-    tile += J * G;
-  }
-}
+namespace b2 {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
@@ -562,10 +303,10 @@ using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const do
 
 template <int KIND, int MODE>
 KernelFn pick_kernel(int pb, int cb) {
-  if (pb == 4 && cb == 4) return factor_kernel<float, float, KIND, MODE>;
-  if (pb == 4 && cb == 8) return factor_kernel<float, double, KIND, MODE>;
-  if (pb == 8 && cb == 4) return factor_kernel<double, float, KIND, MODE>;
-  return factor_kernel<double, double, KIND, MODE>;
+  if (pb == 4 && cb == 4) return ws::factor_kernel<float, float, KIND, MODE>;
+  if (pb == 4 && cb == 8) return ws::factor_kernel<float, double, KIND, MODE>;
+  if (pb == 8 && cb == 4) return ws::factor_kernel<double, float, KIND, MODE>;
+  return ws::factor_kernel<double, double, KIND, MODE>;
 }
 
 KernelFn pick_kernel(int kind, int mode, int pb, int cb) {
@@ -640,7 +381,7 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, 
 b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
   cudaStream_t st = s->ctx->stream;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
+    g.fn[mode]<<<g.grid[mode], ws::kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -846,7 +587,8 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       d.corr = f->d_corr;
       d.lin_pose = f->d_lin_pose;
       d.tile_begin = tile_cursor;
-      d.num_tiles = std::max<uint32_t>(1u, (d.n + kTile - 1) / kTile);
+      d.num_tiles = std::max<uint32_t>(1u, (d.n + ws::kTile - 1) / ws::kTile);
+      d.perm_stride = ws::golden_stride(d.num_tiles);
       d.out_index = static_cast<uint32_t>(g.members[k]);
       tile_cursor += d.num_tiles;
       tile_factor.insert(tile_factor.end(), d.num_tiles, static_cast<uint32_t>(k));
@@ -854,15 +596,22 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     g.num_tiles = tile_cursor;
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb);
-      g.dyn_smem = 0;
+      g.dyn_smem = ws::kRingBytes;
       int per_sm = 0;
-      cudaError_t e = cudaSuccess;
-      if (g.dyn_smem) e = cudaFuncSetAttribute(reinterpret_cast<const void*>(g.fn[mode]), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem));
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], kThreads, g.dyn_smem);
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(g.fn[mode]), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem));
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], ws::kThreads, g.dyn_smem);
       if (e != cudaSuccess || per_sm < 1) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: occupancy query failed (%s)", cudaGetErrorString(e)));
-      g.grid[mode] = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count * per_sm));
+      // persistent: one CTA per SM (the kernel redistributes the SM's whole register file between its warp roles)
+      const uint32_t G = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count));
+      g.grid[mode] = G;
+      // CTA c owns tiles [c T / G, (c + 1) T / G): a factor's partial-sum slots are the CTAs whose range touches it
+      uint32_t c = 0;
       for (auto& d : descs) {
-        d.num_slots[mode] = std::min<uint32_t>(d.num_tiles, g.grid[mode]);
+        while (ws::cta_tile_begin(c + 1, g.num_tiles, G) <= d.tile_begin) c++;
+        uint32_t c_last = c;
+        while (ws::cta_tile_begin(c_last + 1, g.num_tiles, G) < d.tile_begin + d.num_tiles) c_last++;
+        d.cta_first[mode] = c;
+        d.num_slots[mode] = c_last - c + 1;
         d.slot_begin[mode] = slot_cursor;
         slot_cursor += d.num_slots[mode];
       }
@@ -940,6 +689,8 @@ b2_status b2_factor_set_error_device(b2_factor_set* s, const double* d_deltas_ev
 
 b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_linearized* out) {
   B2_REQUIRE(s && deltas && out, "b2_factor_set_linearize: NULL argument");
+  static const bool trace = std::getenv("B2_TRACE") != nullptr;  // development aid: host-side time split of this call on stderr
+  const auto t0 = std::chrono::steady_clock::now();
   B2_CUDA(cudaSetDevice(s->ctx->device));
   cudaStream_t st = s->ctx->stream;
   const size_t F = s->factors.size();
@@ -947,6 +698,7 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
   B2_TRY(s->ctx->ensure_stage(in_bytes + out_bytes, 0));
   char* h = static_cast<char*>(s->ctx->h_stage);
   std::memcpy(h, deltas, in_bytes);
+  auto t1 = t0, t2 = t0;
   if (F <= kZeroCopyMaxFactors) {
     // Small sets: ONE launch and one stream sync.  The staging buffer is pinned, mapped host memory: the kernel reads the
     // poses straight from it (128 B per factor over PCIe) and its per-factor epilogue writes the 1 KiB result record
@@ -956,18 +708,28 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     double* d_in = nullptr;
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
+    t1 = std::chrono::steady_clock::now();
     B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res));
+    t2 = std::chrono::steady_clock::now();
     B2_CUDA(cudaStreamSynchronize(st));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
+    t1 = std::chrono::steady_clock::now();
     B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out));
     B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    t2 = std::chrono::steady_clock::now();
     B2_CUDA(cudaStreamSynchronize(st));
   }
+  const auto t3 = std::chrono::steady_clock::now();
   std::memcpy(out, h + in_bytes, out_bytes);
   for (size_t i = 0; i < F; i++) {
     s->factors[i]->linearized = true;
     std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
+  }
+  if (trace) {
+    const auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    std::fprintf(stderr, "[b2 trace] linearize F=%zu: prepare %.1f us, launch %.1f us, wait %.1f us, finish %.1f us\n", F, us(t0, t1), us(t1, t2), us(t2, t3),
+                 us(t3, std::chrono::steady_clock::now()));
   }
   return B2_OK;
 }
@@ -1004,6 +766,18 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
   std::memcpy(out_errors, h + in_bytes, out_bytes);
   return B2_OK;
 }
+
+#ifdef B2_WS_TIMING
+// development aid (not part of the ABI): fetch and reset the per-CTA timestamps of the last launch
+__attribute__((visibility("default"))) int b2_debug_cta_times(unsigned long long* out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, ws::g_cta_times, sizeof(unsigned long long) * n * 4);
+  std::vector<unsigned long long> init(1024 * 4, 0ull);
+  for (int i = 0; i < 1024; i++) init[i * 4 + 3] = ~0ull;
+  cudaMemcpyToSymbol(ws::g_cta_times, init.data(), sizeof(unsigned long long) * 1024 * 4);
+  return 0;
+}
+#endif
 
 // ---- single-factor conveniences ---------------------------------------------------------------------------------
 
