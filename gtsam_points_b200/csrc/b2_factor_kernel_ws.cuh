@@ -24,36 +24,11 @@
 // it reaches that ring) or at the end of a factor run until the consumer acknowledges; an accumulate warp waits on a ring
 // only while it holds < 32 items and is not finished, in which case its producer is not blocked.  Spins are bounded
 // (trap instead of hanging the GPU).
-#pragma once
+// This file is included once per kernel configuration (no include guard): the includer defines B2_WS_NAMESPACE and the
+// B2_WS_* parameters (see b2_factors.cu), e.g. few fat accumulate warps + many thin probe warps for the kd-tree path.
 
 namespace b2 {
-namespace ws {
-
-#ifndef B2_WS_PRODUCERS
-#define B2_WS_PRODUCERS 8
-#endif
-#ifndef B2_WS_CONSUMERS
-#define B2_WS_CONSUMERS 8
-#endif
-#ifndef B2_WS_REGS_PRODUCER
-#define B2_WS_REGS_PRODUCER 88
-#endif
-#ifndef B2_WS_REGS_CONSUMER
-#define B2_WS_REGS_CONSUMER 168
-#endif
-#ifndef B2_WS_RING
-#define B2_WS_RING 256
-#endif
-#ifndef B2_WS_PPL
-#define B2_WS_PPL 2
-#endif
-#ifndef B2_WS_POSE_SMEM
-#define B2_WS_POSE_SMEM 0  // accumulate warps re-read the pose from shared memory instead of holding it in registers
-#endif
-#ifndef B2_WS_LOOKAHEAD
-#define B2_WS_LOOKAHEAD 0  // 1: accumulate warps issue the gathers of batch k+1 (into registers) before the arithmetic of batch k
-                           // 2: they prefetch batch k+1's operands into L1 instead (no registers held); 0: no lookahead
-#endif
+namespace B2_WS_NAMESPACE {
 
 constexpr int kP = B2_WS_PRODUCERS;
 constexpr int kC = B2_WS_CONSUMERS;
@@ -315,7 +290,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       __syncwarp();
       const double(&R)[9] = *reinterpret_cast<const double(*)[9]>(&sh.probe_pose[p][0]);
       const double(&t)[3] = *reinterpret_cast<const double(*)[3]>(&sh.probe_pose[p][9]);
-      const KdTreeView tv{dg->nodes, dg->leaf_pts, dg->leaf_pts + dg->leaf_n_pad, dg->leaf_pts + 2 * static_cast<size_t>(dg->leaf_n_pad)};
+      const KdTreeView tv{dg->nodes, dg->leaf_pts, static_cast<int>(dg->leaf_f32)};
       const double max_sq = dg->max_sq;
 
       // Virtual tile v of the factor (the CTA owns a contiguous range of them) is physical tile (v * S) mod n_tiles with
@@ -391,7 +366,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
               }
             } else {
               double sq;
-              id[k] = ok[k] ? kdtree_nn1(tv, __dadd_rn(u[k][0], t[0]), __dadd_rn(u[k][1], t[1]), __dadd_rn(u[k][2], t[2]), max_sq, &sq) : -1;
+              id[k] = kdtree_nn1_warp(tv, __dadd_rn(u[k][0], t[0]), __dadd_rn(u[k][1], t[1]), __dadd_rn(u[k][2], t[2]), ok[k], max_sq, &sq);
             }
             if (ok[k]) corr[base + k * 32] = id[k];
           }
@@ -588,5 +563,5 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
   }
 }
 
-}  // namespace ws
+}  // namespace B2_WS_NAMESPACE
 }  // namespace b2

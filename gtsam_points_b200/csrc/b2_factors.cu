@@ -50,8 +50,8 @@ struct FactorDesc {
   double inv_leaf;
   // GICP target
   const KdNodeGPU* nodes;
-  const double* leaf_pts;
-  uint32_t leaf_n_pad;
+  const void* leaf_pts;  // leaf-order point records (float4 or 4 doubles each)
+  uint32_t leaf_f32;
   uint32_t pad1;
   double max_sq;
   // mean(3) | cov(6) | count records: voxels (id order) or target points (leaf order)
@@ -292,7 +292,71 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 
 }  // namespace b2
 
+// ---- kernel configurations -------------------------------------------------------------------------------------
+// VGICP (voxel hash probe): probe and accumulate work are comparable -> 8 probe + 8 accumulate warps.
+#define B2_WS_NAMESPACE ws
+#ifndef B2_WS_PRODUCERS
+#define B2_WS_PRODUCERS 8
+#endif
+#ifndef B2_WS_CONSUMERS
+#define B2_WS_CONSUMERS 8
+#endif
+#ifndef B2_WS_REGS_PRODUCER
+#define B2_WS_REGS_PRODUCER 88
+#endif
+#ifndef B2_WS_REGS_CONSUMER
+#define B2_WS_REGS_CONSUMER 168
+#endif
+#ifndef B2_WS_RING
+#define B2_WS_RING 256
+#endif
+#ifndef B2_WS_PPL
+#define B2_WS_PPL 2
+#endif
+#ifndef B2_WS_LOOKAHEAD
+#define B2_WS_LOOKAHEAD 0  // 1: accumulate warps issue the gathers of batch k+1 (into registers) before the arithmetic of batch k
+                           // 2: they prefetch batch k+1's operands towards the SM instead (no registers held); 0: no lookahead
+#endif
+#ifndef B2_WS_POSE_SMEM
+#define B2_WS_POSE_SMEM 0  // accumulate warps re-read the pose from shared memory instead of holding it in registers
+#endif
 #include "b2_factor_kernel_ws.cuh"
+#undef B2_WS_NAMESPACE
+#undef B2_WS_PRODUCERS
+#undef B2_WS_CONSUMERS
+#undef B2_WS_REGS_PRODUCER
+#undef B2_WS_REGS_CONSUMER
+#undef B2_WS_RING
+#undef B2_WS_PPL
+#undef B2_WS_LOOKAHEAD
+
+// GICP (kd-tree 1-NN): the tree walk is ~100 dependent loads per point, the accumulate work is unchanged -> many thin
+// probe warps (the walk keeps its stack in local memory and needs few registers) feeding 4 fat accumulate warps.
+#define B2_WS_NAMESPACE ws_gicp
+#ifndef B2_WS_GICP_PRODUCERS
+#define B2_WS_GICP_PRODUCERS 28
+#endif
+#ifndef B2_WS_GICP_CONSUMERS
+#define B2_WS_GICP_CONSUMERS 4
+#endif
+#ifndef B2_WS_GICP_REGS_PRODUCER
+#define B2_WS_GICP_REGS_PRODUCER 48
+#endif
+#ifndef B2_WS_GICP_REGS_CONSUMER
+#define B2_WS_GICP_REGS_CONSUMER 168
+#endif
+#ifndef B2_WS_GICP_RING
+#define B2_WS_GICP_RING 128
+#endif
+#define B2_WS_PRODUCERS B2_WS_GICP_PRODUCERS
+#define B2_WS_CONSUMERS B2_WS_GICP_CONSUMERS
+#define B2_WS_REGS_PRODUCER B2_WS_GICP_REGS_PRODUCER
+#define B2_WS_REGS_CONSUMER B2_WS_GICP_REGS_CONSUMER
+#define B2_WS_RING B2_WS_GICP_RING
+#define B2_WS_PPL 1
+#define B2_WS_LOOKAHEAD 0
+#include "b2_factor_kernel_ws.cuh"
+#undef B2_WS_NAMESPACE
 
 namespace b2 {
 
@@ -301,17 +365,34 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*);
 
-template <int KIND, int MODE>
-KernelFn pick_kernel(int pb, int cb) {
-  if (pb == 4 && cb == 4) return ws::factor_kernel<float, float, KIND, MODE>;
-  if (pb == 4 && cb == 8) return ws::factor_kernel<float, double, KIND, MODE>;
-  if (pb == 8 && cb == 4) return ws::factor_kernel<double, float, KIND, MODE>;
-  return ws::factor_kernel<double, double, KIND, MODE>;
+template <int MODE>
+KernelFn pick_vgicp(int pb, int cb) {
+  if (pb == 4 && cb == 4) return ws::factor_kernel<float, float, 0, MODE>;
+  if (pb == 4 && cb == 8) return ws::factor_kernel<float, double, 0, MODE>;
+  if (pb == 8 && cb == 4) return ws::factor_kernel<double, float, 0, MODE>;
+  return ws::factor_kernel<double, double, 0, MODE>;
+}
+template <int MODE>
+KernelFn pick_gicp(int pb, int cb) {
+  if (pb == 4 && cb == 4) return ws_gicp::factor_kernel<float, float, 1, MODE>;
+  if (pb == 4 && cb == 8) return ws_gicp::factor_kernel<float, double, 1, MODE>;
+  if (pb == 8 && cb == 4) return ws_gicp::factor_kernel<double, float, 1, MODE>;
+  return ws_gicp::factor_kernel<double, double, 1, MODE>;
+}
+
+// launch shape of a kernel configuration
+struct KernelShape {
+  int threads, tile;
+  size_t dyn_smem;
+};
+KernelShape kernel_shape(int kind) {
+  if (kind == 0) return {ws::kThreads, ws::kTile, ws::kRingBytes};
+  return {ws_gicp::kThreads, ws_gicp::kTile, ws_gicp::kRingBytes};
 }
 
 KernelFn pick_kernel(int kind, int mode, int pb, int cb) {
-  if (kind == 0) return mode == MODE_LINEARIZE ? pick_kernel<0, MODE_LINEARIZE>(pb, cb) : pick_kernel<0, MODE_ERROR>(pb, cb);
-  return mode == MODE_LINEARIZE ? pick_kernel<1, MODE_LINEARIZE>(pb, cb) : pick_kernel<1, MODE_ERROR>(pb, cb);
+  if (kind == 0) return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE>(pb, cb) : pick_vgicp<MODE_ERROR>(pb, cb);
+  return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE>(pb, cb) : pick_gicp<MODE_ERROR>(pb, cb);
 }
 
 // host-API sets up to this many factors use the zero-copy path (poses read from / results written to mapped pinned memory)
@@ -381,7 +462,7 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, 
 b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
   cudaStream_t st = s->ctx->stream;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], ws::kThreads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
+    g.fn[mode]<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -561,6 +642,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
 
   uint32_t slot_cursor = 0;
   for (auto& g : s->groups) {
+    const KernelShape shape = kernel_shape(g.kind);
     std::vector<FactorDesc> descs(g.members.size());
     std::vector<uint32_t> tile_factor;
     uint32_t tile_cursor = 0;
@@ -580,14 +662,14 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       } else {
         d.nodes = f->tree->d_nodes;
         d.leaf_pts = f->tree->d_leaf_points;
-        d.leaf_n_pad = static_cast<uint32_t>(f->tree->n_pad);
+        d.leaf_f32 = f->tree->leaf_f32 ? 1u : 0u;
         d.max_sq = f->max_corr_sq;
         d.records = f->d_target_records;
       }
       d.corr = f->d_corr;
       d.lin_pose = f->d_lin_pose;
       d.tile_begin = tile_cursor;
-      d.num_tiles = std::max<uint32_t>(1u, (d.n + ws::kTile - 1) / ws::kTile);
+      d.num_tiles = std::max<uint32_t>(1u, (d.n + shape.tile - 1) / shape.tile);
       d.perm_stride = ws::golden_stride(d.num_tiles);
       d.out_index = static_cast<uint32_t>(g.members[k]);
       tile_cursor += d.num_tiles;
@@ -596,10 +678,10 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     g.num_tiles = tile_cursor;
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb);
-      g.dyn_smem = ws::kRingBytes;
+      g.dyn_smem = shape.dyn_smem;
       int per_sm = 0;
       cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(g.fn[mode]), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem));
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], ws::kThreads, g.dyn_smem);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], shape.threads, g.dyn_smem);
       if (e != cudaSuccess || per_sm < 1) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: occupancy query failed (%s)", cudaGetErrorString(e)));
       // persistent: one CTA per SM (the kernel redistributes the SM's whole register file between its warp roles)
       const uint32_t G = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count));

@@ -114,7 +114,8 @@ struct b2_kdtree {
   size_t n = 0;
   size_t num_nodes = 0;
   b2::KdNodeGPU* d_nodes = nullptr;
-  double* d_leaf_points = nullptr;   // 3 planes (x, y, z) of n_pad doubles in leaf order
+  void* d_leaf_points = nullptr;     // leaf-order records: float4 (x, y, z, 0) if leaf_f32 else 4 doubles (x, y, z, 0)
+  bool leaf_f32 = false;             // every coordinate is exactly float32-representable
   size_t n_pad = 0;
   uint32_t* d_leaf_index = nullptr;  // leaf position -> caller index
   std::vector<uint32_t> h_leaf_index;

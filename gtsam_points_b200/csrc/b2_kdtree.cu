@@ -3,7 +3,7 @@
 // Replaces KdTree / KdTree2 behind NearestNeighborSearch::knn_search for k = 1
 // (reference: include/gtsam_points/ann/nearest_neighbor_search.hpp:31-35, ann/kdtree2.hpp:26-61,
 //  builders ann/small_kdtree.hpp:124-274).  The tree shape is our own (balanced median split on the axis of largest
-// extent, <= 16 points per leaf, children adjacent, points re-ordered into leaf order); since the search is exact the
+// extent, <= 8 points per leaf, children adjacent, points re-ordered into leaf order as 16- / 32-byte records); since the search is exact the
 // neighbours are the same as the reference's.
 #include <algorithm>
 #include <numeric>
@@ -15,7 +15,10 @@
 namespace b2 {
 namespace {
 
-constexpr int kMaxLeaf = 16;
+#ifndef B2_KD_LEAF
+#define B2_KD_LEAF 16
+#endif
+constexpr int kMaxLeaf = B2_KD_LEAF;
 
 struct Builder {
   const double* pts;
@@ -69,9 +72,11 @@ struct Builder {
 __global__ void knn1_kernel(KdTreeView tree, const double* __restrict__ q, int qstride, size_t nq, double max_sq, const uint32_t* __restrict__ leaf_index,
                             long long* __restrict__ out_idx, double* __restrict__ out_sq) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= nq) return;
+  const bool active = i < nq;
+  const size_t k = active ? i : 0;
   double sq;
-  const int j = kdtree_nn1(tree, q[i * qstride], q[i * qstride + 1], q[i * qstride + 2], max_sq, &sq);
+  const int j = kdtree_nn1_warp(tree, q[k * qstride], q[k * qstride + 1], q[k * qstride + 2], active, max_sq, &sq);
+  if (!active) return;
   if (out_idx) out_idx[i] = j < 0 ? -1ll : static_cast<long long>(leaf_index[j]);
   if (out_sq) out_sq[i] = sq;
 }
@@ -110,25 +115,37 @@ b2_status b2_kdtree_create(b2_ctx* ctx, const double* points, int point_stride, 
   b.build();
   t->num_nodes = nodes.size();
 
-  std::vector<double> planes(3 * t->n_pad, 0.0);
+  // leaf-order point records: float32 when that is lossless (checked here), else float64
+  bool f32 = true;
+  for (size_t j = 0; j < n && f32; j++) {
+    const double* p = points + j * point_stride;
+    for (int a = 0; a < 3; a++) f32 = f32 && static_cast<double>(static_cast<float>(p[a])) == p[a];
+  }
+  t->leaf_f32 = f32;
+  const size_t rec_bytes = f32 ? 4 * sizeof(float) : 4 * sizeof(double);
+  std::vector<unsigned char> recs(std::max<size_t>(n, 1) * rec_bytes, 0);
   for (size_t j = 0; j < n; j++) {
     const double* p = points + static_cast<size_t>(t->h_leaf_index[j]) * point_stride;
-    planes[j] = p[0];
-    planes[t->n_pad + j] = p[1];
-    planes[2 * t->n_pad + j] = p[2];
+    if (f32) {
+      float* r = reinterpret_cast<float*>(recs.data()) + 4 * j;
+      r[0] = static_cast<float>(p[0]), r[1] = static_cast<float>(p[1]), r[2] = static_cast<float>(p[2]);
+    } else {
+      double* r = reinterpret_cast<double*>(recs.data()) + 4 * j;
+      r[0] = p[0], r[1] = p[1], r[2] = p[2];
+    }
   }
 
   cudaStream_t st = ctx->stream;
   cudaError_t e;
   if ((e = cudaMalloc(reinterpret_cast<void**>(&t->d_nodes), nodes.size() * sizeof(KdNodeGPU))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&t->d_leaf_points), planes.size() * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&t->d_leaf_points, recs.size())) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&t->d_leaf_index), std::max<size_t>(n, 1) * sizeof(uint32_t))) != cudaSuccess) {
     b2_kdtree_destroy(t);
     return fail(B2_ERR_OUT_OF_MEMORY, "b2_kdtree_create: %s", cudaGetErrorString(e));
   }
-  t->device_bytes = nodes.size() * sizeof(KdNodeGPU) + planes.size() * sizeof(double) + n * sizeof(uint32_t);
+  t->device_bytes = nodes.size() * sizeof(KdNodeGPU) + recs.size() + n * sizeof(uint32_t);
   if ((e = cudaMemcpyAsync(t->d_nodes, nodes.data(), nodes.size() * sizeof(KdNodeGPU), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-      (e = cudaMemcpyAsync(t->d_leaf_points, planes.data(), planes.size() * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(t->d_leaf_points, recs.data(), recs.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
       (n > 0 && (e = cudaMemcpyAsync(t->d_leaf_index, t->h_leaf_index.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) ||
       (e = cudaStreamSynchronize(st)) != cudaSuccess) {
     b2_kdtree_destroy(t);
@@ -161,7 +178,7 @@ b2_status b2_kdtree_knn1(const b2_kdtree* t, const double* queries, int query_st
   B2_CUDA(cudaMalloc(&di.p, nq * sizeof(long long)));
   B2_CUDA(cudaMalloc(&ds.p, nq * sizeof(double)));
   B2_CUDA(cudaMemcpyAsync(dq.p, queries, nq * query_stride * sizeof(double), cudaMemcpyHostToDevice, st));
-  KdTreeView view{t->d_nodes, t->d_leaf_points, t->d_leaf_points + t->n_pad, t->d_leaf_points + 2 * t->n_pad};
+  KdTreeView view{t->d_nodes, t->d_leaf_points, t->leaf_f32 ? 1 : 0};
   knn1_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(view, static_cast<const double*>(dq.p), query_stride, nq, max_sq_dist, t->d_leaf_index,
                                                                       static_cast<long long*>(di.p), static_cast<double*>(ds.p));
   B2_CUDA(cudaGetLastError());
