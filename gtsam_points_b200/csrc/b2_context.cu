@@ -80,6 +80,25 @@ b2_status b2_ctx_create(int device, void* stream, b2_ctx** out) {
     return b2::fail(B2_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ep));
   }
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    // completion word for zero-copy host calls: pinned + mapped, plus the device counter that decides who writes it
+    void* h = nullptr;
+    void* d = nullptr;
+    cudaError_t ed = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (ed == cudaSuccess) ed = cudaHostGetDevicePointer(&d, h, 0);
+    if (ed == cudaSuccess) ed = cudaMalloc(reinterpret_cast<void**>(&ctx->d_done_counter), sizeof(unsigned int));
+    if (ed == cudaSuccess) ed = cudaMemset(ctx->d_done_counter, 0, sizeof(unsigned int));
+    if (ed != cudaSuccess) {
+      if (h) cudaFreeHost(h);
+      if (ctx->d_done_counter) cudaFree(ctx->d_done_counter);
+      if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+      delete ctx;
+      return b2::fail(B2_ERR_CUDA, "b2_ctx_create: completion word: %s", cudaGetErrorString(ed));
+    }
+    *static_cast<volatile unsigned int*>(h) = 0u;
+    ctx->h_done = static_cast<volatile unsigned int*>(h);
+    ctx->d_done_flag = static_cast<volatile unsigned int*>(d);
+  }
   *out = ctx;
   return B2_OK;
 }
@@ -90,6 +109,8 @@ b2_status b2_ctx_destroy(b2_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->h_done) cudaFreeHost(const_cast<unsigned int*>(ctx->h_done));
+  if (ctx->d_done_counter) cudaFree(ctx->d_done_counter);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B2_OK;

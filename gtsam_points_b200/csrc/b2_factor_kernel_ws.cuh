@@ -129,9 +129,20 @@ inline uint32_t golden_stride(uint32_t n) {
 // Per-factor flush by the accumulate warpgroup(s): warp butterfly -> cross-warp sum -> fixed slot; the last CTA of the
 // factor sums the slots in slot order and runs the epilogue (H_t = X^T A' X, ...).
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void signal_done(const DoneSignal& sig) {
+  // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
+  if (sig.flag == nullptr) return;
+  const unsigned int prev = atomicAdd(sig.counter, 1u);
+  if (prev == sig.total - 1u) {  // every factor of this host call is done: re-arm the counter, publish the sequence number
+    *sig.counter = 0u;
+    __threadfence_system();
+    *sig.flag = sig.seq;
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int ctid, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-                                             const double* __restrict__ poses_lin) {
+                                             const double* __restrict__ poses_lin, const DoneSignal& sig) {
   constexpr int kCT = kC * 32;
   const int lane = ctid & 31, warp = ctid >> 5;
   const double w = warp_reduce32(v, lane);
@@ -175,6 +186,7 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
     if (ctid == 0) {
       out[d.out_index] = sh.tot[27];
       __threadfence_system();  // `out` may be mapped host memory
+      signal_done(sig);
     }
     consumer_barrier();
     return;
@@ -189,6 +201,7 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
   }
   __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
   consumer_barrier();
+  if (ctid == 0) signal_done(sig);  // every writer of this record fenced before the barrier
   (void)kCT;
 }
 
@@ -238,7 +251,8 @@ __device__ __forceinline__ void prefetch_operands(const Batch& b, const double* 
 template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
-              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out) {
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
+              const DoneSignal sig) {
   __shared__ Shared sh;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double2* const rings = reinterpret_cast<double2*>(dyn_smem);
@@ -557,7 +571,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 2], globaltimer());
       if (lane == 0) atomicMin(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());
 #endif
-      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, poses_lin);
+      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, poses_lin, sig);
       tile = run_end;
     }
   }

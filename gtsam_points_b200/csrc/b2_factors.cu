@@ -22,6 +22,7 @@
 //   * all factors of a set are covered by one launch: the grid walks a tile list (tile -> factor), CTA c takes the
 //     contiguous, balanced tile range [c T / G, (c + 1) T / G), so a CTA meets few factors and each in one run.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,16 @@ namespace b2 {
 constexpr int kAcc = 32;  // accumulator slots per partial record (29 used)
 
 enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
+
+// Optional completion signal of a host call: the CTA that finishes the LAST factor of the call (device counter == total)
+// stores `seq` to a word in pinned, mapped host memory after the results (also mapped) have been fenced at system scope;
+// the host spins on that word instead of paying cudaStreamSynchronize's completion latency.  flag == nullptr: unused.
+struct DoneSignal {
+  unsigned int* counter;
+  volatile unsigned int* flag;
+  unsigned int total;
+  unsigned int seq;
+};
 
 struct FactorDesc {
   const void* pts;    // 3 planes of n_pad
@@ -363,7 +374,7 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
 // ---------------------------------------------------------------------------------------------------------------
-using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*);
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal);
 
 template <int MODE>
 KernelFn pick_vgicp(int pb, int cb) {
@@ -459,10 +470,27 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, size_t n, 
   if (i < n) inv[perm[i]] = static_cast<uint32_t>(i);
 }
 
-b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out) {
+// Wait for the completion word of a zero-copy call (see DoneSignal).  The stream is polled every 1024 spins so that a
+// failed launch / faulting kernel is reported instead of spinning forever.
+b2_status wait_done(b2_ctx* ctx, unsigned int seq) {
+  const volatile unsigned int* flag = ctx->h_done;
+  unsigned spins = 0;
+  while (*flag != seq) {
+    if ((++spins & 0x3FFu) == 0u) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q == cudaSuccess) break;  // everything on the stream has finished: the results are in place
+      if (q != cudaErrorNotReady) return fail(B2_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+    }
+    __builtin_ia32_pause();
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return B2_OK;
+}
+
+b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{nullptr, nullptr, 0u, 0u}) {
   cudaStream_t st = s->ctx->stream;
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out);
+    g.fn[mode]<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, sig);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -791,9 +819,10 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
     t1 = std::chrono::steady_clock::now();
-    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res));
+    const DoneSignal sig{s->ctx->d_done_counter, s->ctx->d_done_flag, static_cast<unsigned int>(F), ++s->ctx->done_seq};
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig));
     t2 = std::chrono::steady_clock::now();
-    B2_CUDA(cudaStreamSynchronize(st));
+    B2_TRY(wait_done(s->ctx, sig.seq));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
     t1 = std::chrono::steady_clock::now();
@@ -837,8 +866,9 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
     double* d_in = nullptr;
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
-    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res));
-    B2_CUDA(cudaStreamSynchronize(st));
+    const DoneSignal sig{s->ctx->d_done_counter, s->ctx->d_done_flag, static_cast<unsigned int>(F), ++s->ctx->done_seq};
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res, sig));
+    B2_TRY(wait_done(s->ctx, sig.seq));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));
     B2_TRY(launch_groups(s, MODE_ERROR, nullptr, s->d_poses_eval, s->d_err));

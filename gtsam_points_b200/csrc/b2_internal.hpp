@@ -81,6 +81,12 @@ struct b2_ctx {
   void* d_stage = nullptr;
   size_t d_stage_bytes = 0;
 
+  // completion word of zero-copy host calls (pinned + mapped) and the device counter behind it
+  volatile unsigned int* h_done = nullptr;
+  volatile unsigned int* d_done_flag = nullptr;  // device alias of h_done
+  unsigned int* d_done_counter = nullptr;
+  unsigned int done_seq = 0;
+
   b2_status ensure_stage(size_t host_bytes, size_t dev_bytes);
 };
 

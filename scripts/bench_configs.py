@@ -190,8 +190,9 @@ def main():
 
             ms = timer.run(step, K, W)
             rec = d_out.cpu().numpy()
+            # algorithmic bytes as in bench.py: the reference's bucket table (load <= 0.5), not this library's sparser one
             V = sum(int(vm.info().num_voxels) for vm, _ in keep)
-            NB = sum(int(vm.info().num_buckets) for vm, _ in keep)
+            NB = sum(1 << max(14, (2 * int(vm.info().num_voxels) - 1).bit_length()) for vm, _ in keep)
             alg = F * n * 48 + NB * 16 + V * 52 + F * 992
             print(json.dumps({
                 "config": "cfg4 (per-GPU share at 8 GPUs): 32 IntegratedVGICPFactors x 200k source points, own 0.5 m map each, ONE launch",

@@ -279,3 +279,41 @@ def test_no_correspondence_and_error_reporting(g, scene):
     fe = g.IntegratedVGICPFactor(0, 1, empty, g.PointCloud(sp, sc))
     fe.linearize({0: np.eye(4), 1: np.eye(4)})
     assert fe.num_inliers() == 0
+
+
+def test_many_small_factors_exercise_run_boundaries(g, scene, oracle_map):
+    """Hundreds of small factors in ONE launch: every CTA walks several factor runs, i.e. the probe->accumulate ring
+    hand-shake (publish / done / ack) and the per-factor flush are crossed many times per CTA; sizes sit on and around
+    the warp-tile and CTA-tile boundaries of the kernel.  Results == per-factor oracle, and a larger set than the
+    zero-copy limit (64) goes through the staged H2D / D2H path."""
+    tp, tc, sp, sc = scene
+    vm = g.GaussianVoxelMapGPU(0.5)
+    vm.insert(g.PointCloud(tp, tc))
+    base = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2049, 0, 7]
+    rng = np.random.default_rng(21)
+    sizes = base + [int(x) for x in rng.integers(1, 700, 200 - len(base))]
+    offs = rng.integers(0, len(sp) - 2100, len(sizes))
+    fs = g.NonlinearFactorSetGPU()
+    ofs, values = [], {}
+    for i, (n, o) in enumerate(zip(sizes, offs)):
+        src = g.PointCloud(sp[o : o + n], sc[o : o + n])
+        osrc = orc.Cloud(sp[o : o + n], sc[o : o + n])
+        f = g.IntegratedVGICPFactor(2 * i, 2 * i + 1, vm, src)
+        of = orc.Factor(oracle_map, osrc, num_threads=1)
+        of._keepalive = osrc
+        assert fs.add(f)
+        ofs.append(of)
+        values[2 * i] = np.eye(4)
+        values[2 * i + 1] = syn.random_pose(rng, 0.01, 0.15)
+    out = fs.linearize(values)
+    assert fs.launch_count() <= 2  # one kernel per storage-type group (the empty cloud may sit in its own group), not one per factor
+    for i, (f, of) in enumerate(zip(fs.factors, ofs)):
+        ref = of.linearize_raw(f.calc_delta(values))
+        assert out[i][121] == ref[121], (i, sizes[i])
+        scale = max(np.abs(ref[:120]).max(), 1e-300)
+        assert np.abs(out[i][:121] - ref[:121]).max() <= TOL * max(scale, abs(ref[120])), (i, sizes[i])
+    errs = fs.error(values)
+    for i, of in enumerate(ofs):
+        eref = of.error(fs.factors[i].calc_delta(values))
+        assert abs(errs[i] - eref) <= TOL * abs(eref) + 1e-300
+    assert np.array_equal(out, fs.linearize(values))  # bit-reproducible
