@@ -332,39 +332,57 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         pt_ahead = next_tile(pt_ahead);
       }
 
+      // coordinates (and, in error mode, the frozen correspondences) of a tile are loaded into registers one tile ahead
+      // of their use: the L2 prefetch above brings them close, this takes the remaining L2 round trip off the chain
+      struct Coords {
+        PT x[kPPL], y[kPPL], z[kPPL];
+        int cid[kPPL];
+      };
+      auto load_coords = [&](uint32_t pt, bool in_run) {
+        Coords c;
+        const uint32_t b0 = pt * kTile + p * kWarpPoints + lane;
+#pragma unroll
+        for (int k = 0; k < kPPL; k++) {
+          const uint32_t i = b0 + k * 32;
+          const uint32_t j = (in_run && i < n) ? i : 0u;  // out-of-range lanes read element 0 (always allocated) and are masked through ok
+          c.x[k] = __ldg(px + j);
+          c.y[k] = __ldg(px + n_pad + j);
+          c.z[k] = __ldg(px + 2 * n_pad + j);
+          c.cid[k] = -1;
+          if (MODE == MODE_ERROR) c.cid[k] = __ldg(corr + j);
+        }
+        return c;
+      };
+#if B2_WS_COORDS_AHEAD
+      Coords c_next = load_coords(pt_cur, tile < run_end);
+#endif
 #pragma unroll 1
       for (; tile < run_end; tile++, pt_cur = next_tile(pt_cur), pt_ahead = next_tile(pt_ahead)) {
         if (tile + kPrefetchAhead < run_end) prefetch_tile(pt_ahead);
         const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
+#if B2_WS_COORDS_AHEAD
+        const Coords c = c_next;
+        c_next = load_coords(next_tile(pt_cur), tile + 1 < run_end);
+#else
+        const Coords c = load_coords(pt_cur, true);
+#endif
         // kPPL independent points per lane: their dependent chains (rotate -> floor -> hash -> bucket group -> match) interleave
         double u[kPPL][3];
         int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
         uint32_t grp_idx[kPPL];
         bool ok[kPPL];
         BucketGroup grp[kPPL];
-        {
-          PT x[kPPL], y[kPPL], z[kPPL];
 #pragma unroll
-          for (int k = 0; k < kPPL; k++) {
-            const uint32_t i = base + k * 32;
-            ok[k] = i < n;
-            const uint32_t j = ok[k] ? i : 0u;  // out-of-range lanes read element 0 (always allocated) and are masked through ok
-            x[k] = __ldg(px + j);
-            y[k] = __ldg(px + n_pad + j);
-            z[k] = __ldg(px + 2 * n_pad + j);
-            id[k] = -1;
-            if (MODE == MODE_ERROR) id[k] = ok[k] ? __ldg(corr + j) : -1;
-          }
-#pragma unroll
-          for (int k = 0; k < kPPL; k++) {
-            rotate_point(R, static_cast<double>(x[k]), static_cast<double>(y[k]), static_cast<double>(z[k]), u[k][0], u[k][1], u[k][2]);
-            if (MODE == MODE_LINEARIZE && KIND == 0) {
-              cx[k] = voxel_coord1(__dadd_rn(u[k][0], t[0]), inv_leaf);
-              cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
-              cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
-              grp_idx[k] = voxel_hash(cx[k], cy[k], cz[k]) & bucket_mask;
-              grp[k] = load_group(buckets, grp_idx[k]);
-            }
+        for (int k = 0; k < kPPL; k++) {
+          ok[k] = base + k * 32 < n;
+          id[k] = (MODE == MODE_ERROR && ok[k]) ? c.cid[k] : -1;
+          rotate_point(R, static_cast<double>(c.x[k]), static_cast<double>(c.y[k]), static_cast<double>(c.z[k]), u[k][0], u[k][1], u[k][2]);
+          if (MODE == MODE_LINEARIZE && KIND == 0) {
+            cx[k] = voxel_coord1(__dadd_rn(u[k][0], t[0]), inv_leaf);
+            cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
+            cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
+            grp_idx[k] = voxel_hash(cx[k], cy[k], cz[k]) & bucket_mask;
+            grp[k] = load_group(buckets, grp_idx[k]);
           }
         }
         uint32_t mask[kPPL], cnt = 0u;
@@ -401,12 +419,14 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             const unsigned long long bits = static_cast<unsigned long long>(base + k * 32) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[k])) << 32);
             ring[slot] = make_double2(u[k][0], u[k][1]);
             ring[kRing + slot] = make_double2(u[k][2], __longlong_as_double(static_cast<long long>(bits)));
+#if B2_WS_PREFETCH_OPERANDS
             // the accumulate warp will gather these: start them towards L2 now
             const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(id[k]) * kRecordDoubles);
             prefetch_l2(rec);
             prefetch_l2(rec + 72);
+#endif
           }
-          if (lane < 12) {
+          if (B2_WS_PREFETCH_OPERANDS && lane < 12) {
             // covariance lines of this 32-point group: 6 planes x 2 halves of 16 points
             const uint32_t half = lane & 1, plane = lane >> 1;
             if ((mask[k] >> (16 * half)) & 0xffffu) prefetch_l2(cv + plane * n_pad + (base - lane) + k * 32 + 16 * half);

@@ -328,6 +328,12 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_WS_LOOKAHEAD 0  // 1: accumulate warps issue the gathers of batch k+1 (into registers) before the arithmetic of batch k
                            // 2: they prefetch batch k+1's operands towards the SM instead (no registers held); 0: no lookahead
 #endif
+#ifndef B2_WS_COORDS_AHEAD
+#define B2_WS_COORDS_AHEAD 0  // 1: probe warps load the coordinates of tile k+1 into registers before working on tile k
+#endif
+#ifndef B2_WS_PREFETCH_OPERANDS
+#define B2_WS_PREFETCH_OPERANDS 1  // probe warps start the voxel record + covariance lines of every hit towards L2
+#endif
 #ifndef B2_WS_POSE_SMEM
 #define B2_WS_POSE_SMEM 0  // accumulate warps re-read the pose from shared memory instead of holding it in registers
 #endif
