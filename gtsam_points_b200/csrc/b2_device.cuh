@@ -8,11 +8,9 @@ namespace b2 {
 // Voxel coordinate of a transformed point: fast_floor(x * inv_leaf_size)
 // (reference: util/fast_floor.hpp:12-15, src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:59-61).
 // Explicitly rounded multiply (no FMA contraction) so that the result is bit-identical to the CPU float64 path.
-__device__ __forceinline__ int voxel_coord1(double q, double inv_leaf) {
-  const double v = __dmul_rn(q, inv_leaf);
-  const int n = __double2int_rz(v);
-  return n - (v < static_cast<double>(n) ? 1 : 0);
-}
+// fast_floor is "truncate, then subtract 1 if the value is below its truncation", i.e. floor(v) for every finite v in int
+// range: one round-toward-minus-infinity conversion gives the same integer.
+__device__ __forceinline__ int voxel_coord1(double q, double inv_leaf) { return __double2int_rd(__dmul_rn(q, inv_leaf)); }
 
 // Bucket index of an integer voxel coordinate.  Our own mixing function (the table layout is private to this
 // library; the reference's XORVector3iHash / boost hash_combine only matter for ITS containers).
@@ -53,16 +51,19 @@ __device__ __forceinline__ BucketGroup load_group(const VoxelBucket* __restrict_
   return r;
 }
 
-// returns id >= 0 (found), -1 (absent), -2 (group full and key not in it: continue with the next group)
+// returns id >= 0 (found), -1 (absent), -2 (group full and key not in it: continue with the next group).
+// Branch-free: a bucket matches iff ((bx ^ x) | (by ^ y) | (bz ^ z)) == 0; ids are >= 0 and an empty bucket carries id -1
+// (whatever its coordinate bytes), so "max over buckets of (match ? id : -1)" is the id of the match or -1, and the group
+// has an empty slot iff the minimum stored id is negative.
 __device__ __forceinline__ int match_group(const BucketGroup& g, int x, int y, int z) {
-  int id = -2;
-  bool has_empty = false;
+  int id = -1, lo = 0;
 #pragma unroll
   for (int k = 0; k < kGroup; k++) {
-    if (g.b[k].w >= 0 && g.b[k].x == x && g.b[k].y == y && g.b[k].z == z) id = g.b[k].w;
-    has_empty |= g.b[k].w < 0;
+    const int diff = (g.b[k].x ^ x) | (g.b[k].y ^ y) | (g.b[k].z ^ z);
+    id = max(id, diff == 0 ? g.b[k].w : -1);
+    lo = min(lo, g.b[k].w);
   }
-  return id >= 0 ? id : (has_empty ? -1 : -2);
+  return id >= 0 ? id : (lo < 0 ? -1 : -2);
 }
 
 // Exact lookup (no max_bucket_scan_count cut-off as in the reference's GPU map: a present voxel is always found).

@@ -39,9 +39,10 @@ constexpr int kTile = kP * kWarpPoints;     // source points per CTA tile
 constexpr uint32_t kPrefetchAhead = 3;      // tiles between the L2 prefetch of a tile's coordinates and their use
 constexpr int kRing = B2_WS_RING;           // items per ring (power of two, >= 64)
 constexpr int kRingsPerConsumer = kP / kC;
+constexpr int kIPL = B2_WS_IPL;             // correspondences per accumulate lane and batch (independent chains interleaved)
 static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
 static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
-static_assert((kRing & (kRing - 1)) == 0 && kRing >= 64 + 2 * kWarpPoints, "ring capacity: a tile's hits + two batches of publication lag + one batch");
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 * kIPL + kWarpPoints, "ring capacity: a tile's hits + one batch of publication lag + one batch");
 static_assert(kWarpPoints * 4 % 128 == 0 || kPPL == 1, "coordinate prefetch works on whole lines");
 constexpr size_t kRingBytes = static_cast<size_t>(kP) * 2 * kRing * sizeof(double2);
 
@@ -74,7 +75,6 @@ struct Backoff {
   }
 };
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kC * 32) : "memory"); }
 
 #ifdef B2_WS_TIMING
@@ -235,16 +235,6 @@ __device__ __forceinline__ void load_operands(Batch& b, const double* __restrict
   b.A = load_cov(cv, n_pad, b.i);
 }
 
-// Pull the operands of a batch into L1 (no registers held): the loads issued one batch later hit there.
-template <typename CT>
-__device__ __forceinline__ void prefetch_operands(const Batch& b, const double* __restrict__ records, const CT* __restrict__ cv, size_t n_pad) {
-  const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(b.id) * kRecordDoubles);
-  prefetch_l1(rec);
-  prefetch_l1(rec + 72);
-#pragma unroll
-  for (int k = 0; k < 6; k++) prefetch_l1(cv + k * n_pad + b.i);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
 // ---------------------------------------------------------------------------------------------------------------
@@ -382,7 +372,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
             cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
             grp_idx[k] = voxel_hash(cx[k], cy[k], cz[k]) & bucket_mask;
+#ifndef B2_WS_DEBUG_NO_PROBE
             grp[k] = load_group(buckets, grp_idx[k]);
+#endif
           }
         }
         uint32_t mask[kPPL], cnt = 0u;
@@ -390,7 +382,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         for (int k = 0; k < kPPL; k++) {
           if (MODE == MODE_LINEARIZE) {
             if (KIND == 0) {
+#ifdef B2_WS_DEBUG_NO_PROBE
+              id[k] = static_cast<int>(grp_idx[k] & 0xffffu);  // measurement aid: no table access, every point "hits" some record
+#else
               id[k] = match_group(grp[k], cx[k], cy[k], cz[k]);
+#endif
               uint32_t g = grp_idx[k];
               while (id[k] == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
                 g = (g + 1) & bucket_mask;
@@ -453,9 +449,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_WS_REGS_CONSUMER));
     const int cw = warp - kP;          // accumulate warp index
     const int ctid = tid - kP * 32;    // thread index within the accumulate group
-    uint32_t head[kRingsPerConsumer], head_pub[kRingsPerConsumer];  // items taken / items handed back to the probe warp
+    uint32_t head[kRingsPerConsumer];  // items taken from each of this warp's rings
 #pragma unroll
-    for (int r = 0; r < kRingsPerConsumer; r++) head[r] = head_pub[r] = 0u;
+    for (int r = 0; r < kRingsPerConsumer; r++) head[r] = 0u;
     uint32_t run = 0u;
     uint32_t tile = tile_lo;
     double acc[kAcc];
@@ -476,17 +472,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           sh.RL[ctid - 12] = __ldg(pl + ((ctid - 12) / 3) * 4 + (ctid - 12) % 3);
       }
       consumer_barrier();
-#if B2_WS_POSE_SMEM
-      // the pose stays in shared memory and is re-read (broadcast) by each batch: 24 registers less per accumulate thread
-      const double(&RL)[9] = sh.RL;
-      const double(&t)[3] = sh.t;
-#else
       double RL[9], t[3];
 #pragma unroll
       for (int k = 0; k < 9; k++) RL[k] = sh.RL[k];
 #pragma unroll
       for (int k = 0; k < 3; k++) t[k] = sh.t[k];
-#endif
 #pragma unroll
       for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
       const double* __restrict__ records = d.records;
@@ -495,33 +485,34 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const uint32_t run_end = min(tile_hi, d.tile_begin + d.num_tiles);
       run++;
 
-      // Strict rotation over this warp's rings, in batches of 32 consecutive items.  The gathers of a batch are issued one
-      // batch ahead of its arithmetic (two register buffers in ping-pong; availability changes timing only, never order).
+      // Strict rotation over this warp's rings, in batches of kBatch = 32 * kIPL consecutive items (always full except for a
+      // probe warp's last batch of the run).  With kIPL = 2 every lane carries two independent correspondences through the
+      // arithmetic at once: their dependent chains interleave (instruction-level parallelism instead of a second warp that
+      // would need its own 58 accumulator registers).
+      constexpr uint32_t kBatch = 32u * kIPL;
+      constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
       uint32_t finished = 0u;
       int r = 0;
-      constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
-      // Takes the next batch in rotation into `dst`.  blocking: wait for it; otherwise give up if it is not there yet.
-      // Returns false when nothing was taken (not ready, or every ring of this run is finished).
-      auto acquire = [&](Batch& dst, bool blocking) -> bool {
-        while (finished != kAllFinished) {
-          while (finished & (1u << r)) r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
-          const int p = cw + r * kC;
-          uint32_t hd = 0u, hd_pub = 0u;
+      while (finished != kAllFinished) {
+        while (finished & (1u << r)) r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+        const int p = cw + r * kC;
+        uint32_t hd = 0u;
 #pragma unroll
-          for (int k = 0; k < kRingsPerConsumer; k++)
-            if (k == r) hd = head[k], hd_pub = head_pub[k];
-          // Hand slots back lazily: everything up to the START of the most recent batch taken from this ring has been through
-          // its arithmetic by now (its shared-memory reads completed long ago), so no fence is needed in this loop.
-          if (lane == 0) st_volatile(&sh.head[p], hd_pub);
-          uint32_t nb = 0u;
-          bool fin = false;
+        for (int k = 0; k < kRingsPerConsumer; k++)
+          if (k == r) hd = head[k];
+        // Hand back the slots of every batch taken so far: the previous batch of this ring went through its arithmetic
+        // before the rotation came back here (its shared-memory reads completed long ago), so this loop needs no fence.
+        if (lane == 0) st_volatile(&sh.head[p], hd);
+        uint32_t nb = 0u;
+        bool fin = false;
+        {
           Backoff bo(32u, 64u);
           while (true) {
             const uint32_t dn = ld_acquire(&sh.done[p]);
             const uint32_t tl = ld_acquire(&sh.tail[p]);
             const uint32_t avail = tl - hd;
-            if (avail >= 32u) {
-              nb = 32u;
+            if (avail >= kBatch) {
+              nb = kBatch;
               break;
             }
             if (dn == run) {  // the probe warp finished this run: `tl` is final
@@ -529,64 +520,49 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
               fin = true;
               break;
             }
-            if (!blocking) return false;
             bo.wait();
           }
-          if (nb > 0u) {
-            load_meta(dst, rings + static_cast<size_t>(p) * 2 * kRing, hd, nb, lane);
-#if B2_WS_LOOKAHEAD == 2
-            prefetch_operands<CT>(dst, records, cv, n_pad);
-#else
-            load_operands<CT>(dst, records, cv, n_pad);
-#endif
-#pragma unroll
-            for (int k = 0; k < kRingsPerConsumer; k++)
-              if (k == r) head_pub[k] = hd, head[k] = hd + nb;
-            hd += nb;
-          }
-          if (fin) {
-            finished |= 1u << r;
-            // the ring is drained for this run: release the probe warp (after the slot reads above: fence + store)
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < kRingsPerConsumer; k++)
-              if (k == r) head_pub[k] = hd;
-            if (lane == 0) {
-              st_volatile(&sh.head[p], hd);
-              st_release(&sh.ack[p], run);
-            }
-          }
-          r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
-          if (nb > 0u) return true;
         }
-        return false;
-      };
-      auto accumulate = [&](Batch& b) {
-#if B2_WS_LOOKAHEAD == 2
-        load_operands<CT>(b, records, cv, n_pad);  // prefetched into L1 one batch ago
+        if (nb > 0u) {
+          Batch b[kIPL];
+#pragma unroll
+          for (int j = 0; j < kIPL; j++) {
+            const uint32_t nj = nb > 32u * j ? min(32u, nb - 32u * j) : 0u;
+            load_meta(b[j], rings + static_cast<size_t>(p) * 2 * kRing, hd + 32u * j, nj, lane);
+#ifndef B2_WS_DEBUG_NO_ACCUM
+            load_operands<CT>(b[j], records, cv, n_pad);  // lanes beyond nj gather element 0 (valid memory), masked below
 #endif
-        if (b.valid) accumulate_point<MODE>(acc, RL, t, b.u0, b.u1, b.u2, b.T, b.A);
-      };
-#if B2_WS_LOOKAHEAD
-      Batch bufA, bufB;
-      bool haveA = false;
-      while (true) {
-        const bool gotB = acquire(bufB, !haveA);
-        if (haveA) accumulate(bufA);
-        if (!gotB) {
-          if (!haveA && finished == kAllFinished) break;
-          haveA = false;
-          continue;
-        }
-        haveA = acquire(bufA, false);
-        accumulate(bufB);
-      }
+          }
+#pragma unroll
+          for (int k = 0; k < kRingsPerConsumer; k++)
+            if (k == r) head[k] = hd + nb;
+#ifdef B2_WS_DEBUG_NO_ACCUM
+#pragma unroll
+          for (int j = 0; j < kIPL; j++)
+            if (b[j].valid) acc[28] += b[j].u0 * 0.0 + 1.0;  // measurement aid: probe-side throughput only
 #else
-      {
-        Batch buf;
-        while (acquire(buf, true)) accumulate(buf);
-      }
+          if (nb == kBatch) {
+            // full batch (uniform branch): no per-lane predicates, the kIPL bodies sit in one basic block and interleave
+#pragma unroll
+            for (int j = 0; j < kIPL; j++) accumulate_point<MODE>(acc, RL, t, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kIPL; j++)
+              if (b[j].valid) accumulate_point<MODE>(acc, RL, t, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
+          }
 #endif
+        }
+        if (fin) {
+          finished |= 1u << r;
+          // the ring is drained for this run: release the probe warp (after the slot reads above: fence + store)
+          __syncwarp();
+          if (lane == 0) {
+            st_volatile(&sh.head[p], hd + nb);
+            st_release(&sh.ack[p], run);
+          }
+        }
+        r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+      }
 #ifdef B2_WS_TIMING
       if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 2], globaltimer());
       if (lane == 0) atomicMin(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());

@@ -217,6 +217,20 @@ __device__ __forceinline__ SourceCov load_cov(const CT* __restrict__ cv, size_t 
   return c;
 }
 
+// 1 / x for a normal, finite x (here: the determinant of a sum of regularised covariances), branch-free: the hardware seed
+// (MUFU.RCP64H, ~20 bits) refined by one cubic and one quadratic Newton step -- the sequence the compiler emits for a
+// float64 division, minus its special-case branch, so that the per-correspondence arithmetic stays ONE basic block and
+// the chains of two correspondences handled by the same lane can interleave.  Result within 1 ulp of 1.0 / x.
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 template <int MODE>
 __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const double (&RL)[9], const double (&t)[3], double v0, double v1, double v2,
                                                  const TargetRec& T, const SourceCov& A) {
@@ -245,7 +259,7 @@ __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const doub
   const double c11 = s00 * s22 - s02 * s02;
   const double c12 = s01 * s02 - s00 * s12;
   const double c22 = s00 * s11 - s01 * s01;
-  const double inv_det = 1.0 / (s00 * c00 + s01 * c01 + s02 * c02);
+  const double inv_det = rcp_nr(s00 * c00 + s01 * c01 + s02 * c02);
   const double m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
   const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
 
@@ -324,18 +338,14 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #ifndef B2_WS_PPL
 #define B2_WS_PPL 2
 #endif
-#ifndef B2_WS_LOOKAHEAD
-#define B2_WS_LOOKAHEAD 0  // 1: accumulate warps issue the gathers of batch k+1 (into registers) before the arithmetic of batch k
-                           // 2: they prefetch batch k+1's operands towards the SM instead (no registers held); 0: no lookahead
+#ifndef B2_WS_IPL
+#define B2_WS_IPL 1  // correspondences per accumulate lane and batch
 #endif
 #ifndef B2_WS_COORDS_AHEAD
 #define B2_WS_COORDS_AHEAD 0  // 1: probe warps load the coordinates of tile k+1 into registers before working on tile k
 #endif
 #ifndef B2_WS_PREFETCH_OPERANDS
 #define B2_WS_PREFETCH_OPERANDS 1  // probe warps start the voxel record + covariance lines of every hit towards L2
-#endif
-#ifndef B2_WS_POSE_SMEM
-#define B2_WS_POSE_SMEM 0  // accumulate warps re-read the pose from shared memory instead of holding it in registers
 #endif
 #include "b2_factor_kernel_ws.cuh"
 #undef B2_WS_NAMESPACE
@@ -345,7 +355,7 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #undef B2_WS_REGS_CONSUMER
 #undef B2_WS_RING
 #undef B2_WS_PPL
-#undef B2_WS_LOOKAHEAD
+#undef B2_WS_IPL
 
 // GICP (kd-tree 1-NN): the tree walk is ~100 dependent loads per point, the accumulate work is unchanged -> many thin
 // probe warps (the walk keeps its stack in local memory and needs few registers) feeding 4 fat accumulate warps.
@@ -371,7 +381,10 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_WS_REGS_CONSUMER B2_WS_GICP_REGS_CONSUMER
 #define B2_WS_RING B2_WS_GICP_RING
 #define B2_WS_PPL 1
-#define B2_WS_LOOKAHEAD 0
+#ifndef B2_WS_GICP_IPL
+#define B2_WS_GICP_IPL 1
+#endif
+#define B2_WS_IPL B2_WS_GICP_IPL
 #include "b2_factor_kernel_ws.cuh"
 #undef B2_WS_NAMESPACE
 
