@@ -124,7 +124,6 @@ struct b2_kdtree {
   bool leaf_f32 = false;             // every coordinate is exactly float32-representable
   size_t n_pad = 0;
   uint32_t* d_leaf_index = nullptr;  // leaf position -> caller index
-  std::vector<uint32_t> h_leaf_index;
   size_t device_bytes = 0;
 };
 

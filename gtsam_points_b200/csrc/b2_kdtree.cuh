@@ -17,7 +17,7 @@
 
 namespace b2 {
 
-constexpr int kKdStackDepth = 40;  // > log2(2^31 / leaf) with margin
+constexpr int kKdStackDepth = 52;  // the device build splits on 48 Morton bits: at most 49 levels
 
 struct KdTreeView {
   const KdNodeGPU* nodes;
