@@ -2,20 +2,19 @@
 //
 // Replaces KdTree / KdTree2 behind NearestNeighborSearch::knn_search for k = 1
 // (reference: include/gtsam_points/ann/nearest_neighbor_search.hpp:31-35, ann/kdtree2.hpp:26-61,
-//  builders ann/small_kdtree.hpp:124-274).  The tree shape is our own; since the search is exact the neighbours are the
-// same as the reference's for any valid tree.
+//  builders ann/small_kdtree.hpp:124-274).  The tree shape is our own (balanced: median split on the axis of largest
+// extent, <= 16 points per leaf, children adjacent, points re-ordered into leaf order); since the search is exact the
+// neighbours are the same as the reference's for any valid tree.
 //
-// Build (all on the device, deterministic, ~1 ms for 500k points instead of 0.36 s on the host):
-//   1. bounding box; every coordinate is quantised to 16 bits per axis against the threshold grid
-//      T_a(Q) = min_a + Q * cell_a, with the quantum CORRECTED so that T_a(q) <= x < T_a(q + 1) holds exactly in floating point;
-//   2. 48-bit Morton keys (x, y, z bits interleaved, x most significant), stable radix sort of (key, index): the sorted
-//      order is the leaf order;
-//   3. top-down, one level per pass: a node is a range of the sorted keys; it becomes a leaf if it holds <= 16 points or
-//      all its keys are equal, else it is split at the most significant key bit in which its first and last key differ --
-//      the children are the sub-ranges with that bit clear / set (binary search), allocated as an adjacent pair by an
-//      exclusive scan over the level (deterministic numbering), and the split plane is x_axis = T_axis(Q) with Q the
-//      quantum prefix of the upper half: by (1) every point of the lower child is strictly below it and every point of the
-//      upper child is on or above it, which is all the exact search needs.
+// Build, all on the device, one tree level per pass (~16 passes for 500k points), deterministic:
+//   a node is a contiguous range of the point permutation `order`.  Per level: (1) every position finds its node (binary
+//   search in the level's sorted range list) and folds its coordinates into the node's bounding box (atomic min / max on
+//   order-preserving integer images of the doubles); (2) every node bigger than a leaf picks its axis of largest extent;
+//   (3) every position of such a node emits the order-preserving image of its coordinate along that axis as a 64-bit key;
+//   (4) ONE stable segmented radix sort (CUB) sorts all those nodes' ranges by key at once; (5) the node is split at the
+//   median position: threshold = the median element's coordinate (exact data value), so every point of the lower child is
+//   <= threshold and every point of the upper child >= threshold -- all the exact search needs; children are allocated as
+//   an adjacent pair by an exclusive scan over the level (deterministic numbering).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -32,123 +31,115 @@ namespace {
 #define B2_KD_LEAF 16
 #endif
 constexpr int kMaxLeaf = B2_KD_LEAF;
-constexpr int kQuantBits = 16;
-constexpr uint32_t kQuantMax = (1u << kQuantBits) - 1u;
 
-struct Grid {
-  double mn[3];
-  double cell[3];
-  double inv_cell[3];
-};
-
-__device__ __forceinline__ double grid_threshold(const Grid& g, int axis, uint32_t Q) { return __dadd_rn(g.mn[axis], __dmul_rn(static_cast<double>(Q), g.cell[axis])); }
-
-// order-preserving map double -> uint64 (for atomicMin / atomicMax on coordinates)
-__device__ __forceinline__ unsigned long long ordered_bits(double v) {
-  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+// order-preserving map double -> uint64 (sort keys, atomicMin / atomicMax on coordinates)
+__host__ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  unsigned long long b;
+#ifdef __CUDA_ARCH__
+  b = static_cast<unsigned long long>(__double_as_longlong(v));
+#else
+  std::memcpy(&b, &v, sizeof(b));
+#endif
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-inline double from_ordered_bits(unsigned long long o) {
-  const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
-  double v;
-  std::memcpy(&v, &b, sizeof(v));
-  return v;
-}
-
-__global__ void bbox_kernel(const double* __restrict__ pts, int stride, size_t n, unsigned long long* __restrict__ mnmx /* min xyz | max xyz, ordered bits */,
-                            unsigned int* __restrict__ not_f32) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
-  bool lossy = false;
-  if (i < n) {
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const double v = pts[i * stride + a];
-      lo[a] = hi[a] = ordered_bits(v);
-      lossy |= static_cast<double>(static_cast<float>(v)) != v;
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
-      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
-    }
-  }
-  lossy = __any_sync(0xffffffffu, lossy);
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      atomicMin(&mnmx[a], lo[a]);
-      atomicMax(&mnmx[3 + a], hi[a]);
-    }
-    if (lossy) atomicOr(not_f32, 1u);
-  }
-}
-
-__device__ __forceinline__ unsigned long long spread3(uint32_t v) {  // 16 bits -> every third bit
-  unsigned long long x = v & 0xffffull;
-  x = (x | (x << 32)) & 0x001f00000000ffffull;
-  x = (x | (x << 16)) & 0x001f0000ff0000ffull;
-  x = (x | (x << 8)) & 0x100f00f00f00f00full;
-  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
-  x = (x | (x << 2)) & 0x1249249249249249ull;
-  return x;
-}
-
-__global__ void morton_kernel(const double* __restrict__ pts, int stride, size_t n, Grid g, unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= n) return;
-  uint32_t q[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    const double v = pts[i * stride + a];
-    double f = floor((v - g.mn[a]) * g.inv_cell[a]);
-    f = f < 0.0 ? 0.0 : (f > static_cast<double>(kQuantMax) ? static_cast<double>(kQuantMax) : f);
-    uint32_t Q = static_cast<uint32_t>(f);
-    // make the quantum consistent with the threshold grid: T(Q) <= v < T(Q + 1), exactly
-    while (Q > 0u && v < grid_threshold(g, a, Q)) Q--;
-    while (Q < kQuantMax && v >= grid_threshold(g, a, Q + 1u)) Q++;
-    q[a] = Q;
-  }
-  keys[i] = (spread3(q[0]) << 2) | (spread3(q[1]) << 1) | spread3(q[2]);
-  idx[i] = static_cast<uint32_t>(i);
 }
 
 struct Range {
   uint32_t first, last;
 };
 
-// One level of the top-down build: decide leaf / internal for every node of the level, find the split of internal nodes.
-__global__ void classify_level_kernel(const unsigned long long* __restrict__ keys, const Range* __restrict__ level, uint32_t count, uint32_t* __restrict__ flag,
-                                      uint32_t* __restrict__ split, int* __restrict__ bit) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
-  const Range r = level[k];
-  const unsigned long long kf = keys[r.first], kl = keys[r.last - 1u];
-  if (r.last - r.first <= static_cast<uint32_t>(kMaxLeaf) || kf == kl) {
-    flag[k] = 0u;
-    return;
-  }
-  const int b = 63 - __clzll(static_cast<long long>(kf ^ kl));  // most significant differing bit; higher bits are common to the range
-  const unsigned long long pivot = ((kl >> b) << b);            // smallest key of the upper half
-  uint32_t lo = r.first, hi = r.last - 1u;                      // keys[lo] < pivot <= keys[hi]
-  while (hi - lo > 1u) {
+// the range of the level that contains position `pos` (ranges are sorted by `first` and disjoint), or -1
+__device__ __forceinline__ int find_range(const Range* __restrict__ level, uint32_t count, uint32_t pos) {
+  uint32_t lo = 0u, hi = count;  // first index with level[idx].first > pos
+  while (lo < hi) {
     const uint32_t mid = lo + (hi - lo) / 2u;
-    if (keys[mid] < pivot)
-      lo = mid;
+    if (level[mid].first <= pos)
+      lo = mid + 1u;
     else
       hi = mid;
   }
-  flag[k] = 1u;
-  split[k] = hi;
-  bit[k] = b;
+  if (lo == 0u) return -1;
+  const uint32_t k = lo - 1u;
+  return pos < level[k].last ? static_cast<int>(k) : -1;
 }
 
-__global__ void emit_level_kernel(const unsigned long long* __restrict__ keys, const Range* __restrict__ level, uint32_t count, uint32_t level_base,
-                                  const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ split, const int* __restrict__ bit,
-                                  uint32_t child_base, Grid g, KdNodeGPU* __restrict__ nodes, Range* __restrict__ next) {
+__global__ void scan_points_kernel(const double* __restrict__ pts, int stride, size_t n, unsigned int* __restrict__ not_f32, unsigned int* __restrict__ not_finite,
+                                   uint32_t* __restrict__ order) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  bool lossy = false, bad = false;
+  if (i < n) {
+    order[i] = static_cast<uint32_t>(i);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const double v = pts[i * stride + a];
+      lossy |= static_cast<double>(static_cast<float>(v)) != v;
+      bad |= !isfinite(v);
+    }
+  }
+  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) atomicOr(not_f32, 1u);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_finite, 1u);
+}
+
+__global__ void classify_level_kernel(const Range* __restrict__ level, uint32_t count, uint32_t* __restrict__ flag) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) flag[k] = (level[k].last - level[k].first > static_cast<uint32_t>(kMaxLeaf)) ? 1u : 0u;
+}
+
+__global__ void init_bbox_kernel(unsigned long long* __restrict__ bbox, uint32_t internal) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < internal * 6u) bbox[k] = (k % 6u) < 3u ? ~0ull : 0ull;  // min x y z | max x y z
+}
+
+__global__ void bbox_level_kernel(const double* __restrict__ pts, int stride, size_t n, const uint32_t* __restrict__ order, const Range* __restrict__ level,
+                                  uint32_t count, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank, unsigned long long* __restrict__ bbox) {
+  const size_t pos = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (pos >= n) return;
+  const int k = find_range(level, count, static_cast<uint32_t>(pos));
+  if (k < 0 || !flag[k]) return;
+  const double* p = pts + static_cast<size_t>(order[pos]) * stride;
+  unsigned long long* b = bbox + static_cast<size_t>(rank[k]) * 6;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const unsigned long long o = ordered_bits(p[a]);
+    atomicMin(&b[a], o);
+    atomicMax(&b[3 + a], o);
+  }
+}
+
+__device__ __forceinline__ double from_ordered_bits_dev(unsigned long long o) {
+  const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+
+// per internal node (indexed by rank): axis of largest extent + the segment it occupies in `order`
+__global__ void axis_level_kernel(const Range* __restrict__ level, uint32_t count, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank,
+                                  const unsigned long long* __restrict__ bbox, int* __restrict__ axis, uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ seg_end) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count || !flag[k]) return;
+  const uint32_t r = rank[k];
+  const unsigned long long* b = bbox + static_cast<size_t>(r) * 6;
+  double ext[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) ext[a] = from_ordered_bits_dev(b[3 + a]) - from_ordered_bits_dev(b[a]);
+  int ax = 0;
+  if (ext[1] > ext[ax]) ax = 1;
+  if (ext[2] > ext[ax]) ax = 2;
+  axis[r] = ax;
+  seg_begin[r] = level[k].first;
+  seg_end[r] = level[k].last;
+}
+
+__global__ void keys_level_kernel(const double* __restrict__ pts, int stride, size_t n, const uint32_t* __restrict__ order, const Range* __restrict__ level,
+                                  uint32_t count, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank, const int* __restrict__ axis,
+                                  unsigned long long* __restrict__ keys) {
+  const size_t pos = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (pos >= n) return;
+  const int k = find_range(level, count, static_cast<uint32_t>(pos));
+  keys[pos] = (k >= 0 && flag[k]) ? ordered_bits(pts[static_cast<size_t>(order[pos]) * stride + axis[rank[k]]]) : 0ull;
+}
+
+__global__ void emit_level_kernel(const double* __restrict__ pts, int stride, const uint32_t* __restrict__ order_sorted, const Range* __restrict__ level, uint32_t count,
+                                  uint32_t level_base, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank, const int* __restrict__ axis,
+                                  uint32_t child_base, KdNodeGPU* __restrict__ nodes, Range* __restrict__ next) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
   const Range r = level[k];
@@ -158,18 +149,14 @@ __global__ void emit_level_kernel(const unsigned long long* __restrict__ keys, c
     nd.a = r.first;
     nd.b = 4u + (r.last - r.first);
   } else {
-    const int b = bit[k];
-    const int axis = 2 - (b % 3);   // key bit 3c+2 is x, 3c+1 is y, 3c is z
-    const int cb = b / 3;           // coordinate bit
-    // quantum prefix of the upper half along `axis`: the coordinate bits above and including cb of its smallest key
-    const unsigned long long ks = keys[split[k]];
-    uint32_t q = 0u;
-    for (int c = kQuantBits - 1; c >= cb; c--) q |= static_cast<uint32_t>((ks >> (3 * c + (2 - axis))) & 1ull) << c;
-    nd.thresh = grid_threshold(g, axis, q);
-    nd.a = child_base + 2u * rank[k];
-    nd.b = static_cast<uint32_t>(axis);
-    next[2u * rank[k]] = Range{r.first, split[k]};
-    next[2u * rank[k] + 1u] = Range{split[k], r.last};
+    const uint32_t rk = rank[k];
+    const uint32_t mid = r.first + (r.last - r.first) / 2u;
+    const int ax = axis[rk];
+    nd.thresh = pts[static_cast<size_t>(order_sorted[mid]) * stride + ax];  // lower child <= thresh <= upper child
+    nd.a = child_base + 2u * rk;
+    nd.b = static_cast<uint32_t>(ax);
+    next[2u * rk] = Range{r.first, mid};
+    next[2u * rk + 1u] = Range{mid, r.last};
   }
   nodes[level_base + k] = nd;
 }
@@ -251,86 +238,97 @@ b2_status b2_kdtree_create(b2_ctx* ctx, const double* points, int point_stride, 
   }
 
   const unsigned grid_n = static_cast<unsigned>((n + 255) / 256);
-  DevBuf d_pts, d_mnmx, d_flag32, d_keys, d_keys_sorted, d_idx, d_tmp, d_levelA, d_levelB, d_flag, d_rank, d_split, d_bit, d_scan_tmp;
+  DevBuf d_pts, d_flags2, d_orderB, d_keysA, d_keysB, d_tmp, d_levelA, d_levelB, d_flag, d_rank, d_bbox, d_axis, d_segb, d_sege, d_scan_tmp;
   KD_CUDA(cudaMalloc(&d_pts.p, n * point_stride * sizeof(double)));
   KD_CUDA(cudaMemcpyAsync(d_pts.p, points, n * point_stride * sizeof(double), cudaMemcpyHostToDevice, st));
   const double* dp = static_cast<const double*>(d_pts.p);
 
-  // 1. bounding box + "is every coordinate float32-representable"
-  unsigned long long h_mnmx[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
-  unsigned int h_not_f32 = 0u;
-  KD_CUDA(cudaMalloc(&d_mnmx.p, sizeof(h_mnmx)));
-  KD_CUDA(cudaMalloc(&d_flag32.p, sizeof(unsigned int)));
-  KD_CUDA(cudaMemcpyAsync(d_mnmx.p, h_mnmx, sizeof(h_mnmx), cudaMemcpyHostToDevice, st));
-  KD_CUDA(cudaMemsetAsync(d_flag32.p, 0, sizeof(unsigned int), st));
-  bbox_kernel<<<grid_n, 256, 0, st>>>(dp, point_stride, n, static_cast<unsigned long long*>(d_mnmx.p), static_cast<unsigned int*>(d_flag32.p));
-  KD_CUDA(cudaGetLastError());
-  KD_CUDA(cudaMemcpyAsync(h_mnmx, d_mnmx.p, sizeof(h_mnmx), cudaMemcpyDeviceToHost, st));
-  KD_CUDA(cudaMemcpyAsync(&h_not_f32, d_flag32.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-  KD_CUDA(cudaStreamSynchronize(st));
-  t->leaf_f32 = h_not_f32 == 0u;
-  Grid g;
-  for (int a = 0; a < 3; a++) {
-    const double mn = from_ordered_bits(h_mnmx[a]), mx = from_ordered_bits(h_mnmx[3 + a]);
-    if (!(std::isfinite(mn) && std::isfinite(mx))) return bail(fail(B2_ERR_INVALID_ARGUMENT, "b2_kdtree_create: non-finite coordinate"));
-    g.mn[a] = mn;
-    g.cell[a] = mx > mn ? (mx - mn) / static_cast<double>(1u << kQuantBits) : 1.0;
-    g.inv_cell[a] = 1.0 / g.cell[a];
-  }
-
-  // 2. Morton keys, stable sort: the sorted order is the leaf order
-  KD_CUDA(cudaMalloc(&d_keys.p, n * sizeof(unsigned long long)));
-  KD_CUDA(cudaMalloc(&d_keys_sorted.p, n * sizeof(unsigned long long)));
-  KD_CUDA(cudaMalloc(&d_idx.p, n * sizeof(uint32_t)));
+  // point scan: identity permutation, "is every coordinate float32-representable", "is every coordinate finite"
   KD_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_leaf_index), n * sizeof(uint32_t)));
-  morton_kernel<<<grid_n, 256, 0, st>>>(dp, point_stride, n, g, static_cast<unsigned long long*>(d_keys.p), static_cast<uint32_t*>(d_idx.p));
+  KD_CUDA(cudaMalloc(&d_orderB.p, n * sizeof(uint32_t)));
+  KD_CUDA(cudaMalloc(&d_flags2.p, 2 * sizeof(unsigned int)));
+  KD_CUDA(cudaMemsetAsync(d_flags2.p, 0, 2 * sizeof(unsigned int), st));
+  uint32_t* order = t->d_leaf_index;                     // the two permutation buffers swap roles level by level;
+  uint32_t* order_alt = static_cast<uint32_t*>(d_orderB.p);  // the final one is copied into t->d_leaf_index if needed
+  scan_points_kernel<<<grid_n, 256, 0, st>>>(dp, point_stride, n, static_cast<unsigned int*>(d_flags2.p), static_cast<unsigned int*>(d_flags2.p) + 1, order);
   KD_CUDA(cudaGetLastError());
-  size_t tmp_bytes = 0;
-  KD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<const unsigned long long*>(d_keys.p), static_cast<unsigned long long*>(d_keys_sorted.p),
-                                          static_cast<const uint32_t*>(d_idx.p), t->d_leaf_index, static_cast<int>(n), 0, 3 * kQuantBits, st));
-  KD_CUDA(cudaMalloc(&d_tmp.p, std::max<size_t>(tmp_bytes, 16)));
-  KD_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, static_cast<const unsigned long long*>(d_keys.p), static_cast<unsigned long long*>(d_keys_sorted.p),
-                                          static_cast<const uint32_t*>(d_idx.p), t->d_leaf_index, static_cast<int>(n), 0, 3 * kQuantBits, st));
-  const unsigned long long* keys = static_cast<const unsigned long long*>(d_keys_sorted.p);
+  unsigned int h_flags2[2] = {0u, 0u};
+  KD_CUDA(cudaMemcpyAsync(h_flags2, d_flags2.p, sizeof(h_flags2), cudaMemcpyDeviceToHost, st));
+  KD_CUDA(cudaStreamSynchronize(st));
+  if (h_flags2[1]) return bail(fail(B2_ERR_INVALID_ARGUMENT, "b2_kdtree_create: non-finite coordinate"));
+  t->leaf_f32 = h_flags2[0] == 0u;
 
-  // 3. top-down build, one level per pass (at most 3 * kQuantBits + 1 levels)
   const size_t max_nodes = 2 * n + 1;
+  const size_t max_level = n / 2 + 2;  // nodes per level (every node of a level below the root holds >= kMaxLeaf / 2 >= 2 points)
   KD_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_nodes), max_nodes * sizeof(KdNodeGPU)));
-  KD_CUDA(cudaMalloc(&d_levelA.p, (n + 1) * sizeof(Range)));
-  KD_CUDA(cudaMalloc(&d_levelB.p, (n + 1) * sizeof(Range)));
-  KD_CUDA(cudaMalloc(&d_flag.p, (n + 1) * sizeof(uint32_t)));
-  KD_CUDA(cudaMalloc(&d_rank.p, (n + 1) * sizeof(uint32_t)));
-  KD_CUDA(cudaMalloc(&d_split.p, (n + 1) * sizeof(uint32_t)));
-  KD_CUDA(cudaMalloc(&d_bit.p, (n + 1) * sizeof(int)));
+  KD_CUDA(cudaMalloc(&d_keysA.p, n * sizeof(unsigned long long)));
+  KD_CUDA(cudaMalloc(&d_keysB.p, n * sizeof(unsigned long long)));
+  KD_CUDA(cudaMalloc(&d_levelA.p, max_level * sizeof(Range)));
+  KD_CUDA(cudaMalloc(&d_levelB.p, max_level * sizeof(Range)));
+  KD_CUDA(cudaMalloc(&d_flag.p, max_level * sizeof(uint32_t)));
+  KD_CUDA(cudaMalloc(&d_rank.p, max_level * sizeof(uint32_t)));
+  KD_CUDA(cudaMalloc(&d_bbox.p, max_level * 6 * sizeof(unsigned long long)));
+  KD_CUDA(cudaMalloc(&d_axis.p, max_level * sizeof(int)));
+  KD_CUDA(cudaMalloc(&d_segb.p, max_level * sizeof(uint32_t)));
+  KD_CUDA(cudaMalloc(&d_sege.p, max_level * sizeof(uint32_t)));
   size_t scan_bytes = 0;
-  KD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<const uint32_t*>(d_flag.p), static_cast<uint32_t*>(d_rank.p), static_cast<int>(n + 1), st));
+  KD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<const uint32_t*>(d_flag.p), static_cast<uint32_t*>(d_rank.p), static_cast<int>(max_level), st));
   KD_CUDA(cudaMalloc(&d_scan_tmp.p, std::max<size_t>(scan_bytes, 16)));
+  size_t sort_bytes = 0;
   const Range root{0u, static_cast<uint32_t>(n)};
   KD_CUDA(cudaMemcpyAsync(d_levelA.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
   Range* cur = static_cast<Range*>(d_levelA.p);
   Range* nxt = static_cast<Range*>(d_levelB.p);
+  uint32_t* flag = static_cast<uint32_t*>(d_flag.p);
+  uint32_t* rank = static_cast<uint32_t*>(d_rank.p);
   uint32_t count = 1u, level_base = 0u, total = 1u;
   int depth = 0;
   while (count > 0u) {
     if (++depth > kKdStackDepth) return bail(fail(B2_ERR_INVALID_STATE, "b2_kdtree_create: tree deeper than the traversal stack (%d levels)", kKdStackDepth));
     const unsigned gl = (count + 255u) / 256u;
-    classify_level_kernel<<<gl, 256, 0, st>>>(keys, cur, count, static_cast<uint32_t*>(d_flag.p), static_cast<uint32_t*>(d_split.p), static_cast<int*>(d_bit.p));
+    classify_level_kernel<<<gl, 256, 0, st>>>(cur, count, flag);
     KD_CUDA(cudaGetLastError());
-    KD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, scan_bytes, static_cast<const uint32_t*>(d_flag.p), static_cast<uint32_t*>(d_rank.p), static_cast<int>(count), st));
-    emit_level_kernel<<<gl, 256, 0, st>>>(keys, cur, count, level_base, static_cast<const uint32_t*>(d_flag.p), static_cast<const uint32_t*>(d_rank.p),
-                                          static_cast<const uint32_t*>(d_split.p), static_cast<const int*>(d_bit.p), total, g, t->d_nodes, nxt);
-    KD_CUDA(cudaGetLastError());
-    uint32_t last_rank = 0u, last_flag = 0u;  // number of internal nodes of this level = rank[count-1] + flag[count-1]
-    KD_CUDA(cudaMemcpyAsync(&last_rank, static_cast<uint32_t*>(d_rank.p) + (count - 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    KD_CUDA(cudaMemcpyAsync(&last_flag, static_cast<uint32_t*>(d_flag.p) + (count - 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    KD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, scan_bytes, flag, rank, static_cast<int>(count), st));
+    uint32_t last_rank = 0u, last_flag = 0u;  // number of nodes to split on this level = rank[count-1] + flag[count-1]
+    KD_CUDA(cudaMemcpyAsync(&last_rank, rank + (count - 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    KD_CUDA(cudaMemcpyAsync(&last_flag, flag + (count - 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     KD_CUDA(cudaStreamSynchronize(st));
     const uint32_t internal = last_rank + last_flag;
+    if (internal > 0u) {
+      init_bbox_kernel<<<(internal * 6u + 255u) / 256u, 256, 0, st>>>(static_cast<unsigned long long*>(d_bbox.p), internal);
+      bbox_level_kernel<<<grid_n, 256, 0, st>>>(dp, point_stride, n, order, cur, count, flag, rank, static_cast<unsigned long long*>(d_bbox.p));
+      axis_level_kernel<<<gl, 256, 0, st>>>(cur, count, flag, rank, static_cast<const unsigned long long*>(d_bbox.p), static_cast<int*>(d_axis.p),
+                                            static_cast<uint32_t*>(d_segb.p), static_cast<uint32_t*>(d_sege.p));
+      keys_level_kernel<<<grid_n, 256, 0, st>>>(dp, point_stride, n, order, cur, count, flag, rank, static_cast<const int*>(d_axis.p),
+                                                static_cast<unsigned long long*>(d_keysA.p));
+      KD_CUDA(cudaGetLastError());
+      // positions outside the sorted segments (finished leaves) keep their element
+      KD_CUDA(cudaMemcpyAsync(order_alt, order, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      size_t need = 0;
+      KD_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, need, static_cast<const unsigned long long*>(d_keysA.p), static_cast<unsigned long long*>(d_keysB.p),
+                                                        static_cast<const uint32_t*>(order), order_alt, static_cast<int>(n), static_cast<int>(internal),
+                                                        static_cast<const uint32_t*>(d_segb.p), static_cast<const uint32_t*>(d_sege.p), st));
+      if (need > sort_bytes) {
+        KD_CUDA(cudaStreamSynchronize(st));
+        if (d_tmp.p) cudaFree(d_tmp.p);
+        d_tmp.p = nullptr;
+        KD_CUDA(cudaMalloc(&d_tmp.p, need));
+        sort_bytes = need;
+      }
+      KD_CUDA(cub::DeviceSegmentedSort::StableSortPairs(d_tmp.p, need, static_cast<const unsigned long long*>(d_keysA.p), static_cast<unsigned long long*>(d_keysB.p),
+                                                        static_cast<const uint32_t*>(order), order_alt, static_cast<int>(n), static_cast<int>(internal),
+                                                        static_cast<const uint32_t*>(d_segb.p), static_cast<const uint32_t*>(d_sege.p), st));
+      std::swap(order, order_alt);
+    }
+    emit_level_kernel<<<gl, 256, 0, st>>>(dp, point_stride, order, cur, count, level_base, flag, rank, static_cast<const int*>(d_axis.p), total, t->d_nodes, nxt);
+    KD_CUDA(cudaGetLastError());
     level_base = total;
     total += 2u * internal;
     count = 2u * internal;
     std::swap(cur, nxt);
   }
   t->num_nodes = total;
+  if (order != t->d_leaf_index) KD_CUDA(cudaMemcpyAsync(t->d_leaf_index, order, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
 
   // leaf-order point records: float32 when that is lossless, else float64
   const size_t rec_bytes = t->leaf_f32 ? 4 * sizeof(float) : 4 * sizeof(double);
