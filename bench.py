@@ -137,10 +137,25 @@ def ncu_traffic():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference's OpenMP CPU path, all host cores
 # ------------------------------------------------------------------------------------------------------------------
+def cpu_threads(orc) -> int:
+    """One OpenMP thread per PHYSICAL core: the float64 loop does not gain from SMT siblings (measured on the B200 host:
+    64 threads on 64 cores 20 M correspondences/s, 128 threads on the same cores 4.3 M/s), and the reference arm must show
+    the CPU path at its best."""
+    try:
+        import psutil
+
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            return max(1, min(int(phys), orc.max_threads()))
+    except Exception:
+        pass
+    return orc.max_threads()
+
+
 def time_cpu(tp, tc, sp, sc, poses, warmup: int, steps: int):
     import oracle_lib as orc
 
-    threads = orc.max_threads()
+    threads = cpu_threads(orc)
     vm = orc.VoxelMap(RESOLUTION)
     tgt = orc.Cloud(tp, tc)
     vm.insert(tgt)
