@@ -222,6 +222,10 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at init when NCCL_DEBUG=VERSION is in the environment; stdout must carry
+        # exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -284,6 +288,17 @@ def run_gpu(args):
         step_ms = np.array([a.elapsed_time(b) for a, b in ev])
         dev_total_ms = float(step_ms.sum())
         rec = sset.d_all.cpu().numpy()
+        exchange_path = "peer stores in the kernel epilogue (NVLink) + flag wait" if sset.exchange is not None else "ONE all-reduce of [N x 128] f64 (NCCL)"
+        if world > 1 and sset.exchange is not None:
+            # untimed cross-check: the fused peer-memory exchange must deliver exactly what the all-reduce path delivers
+            saved, sset.exchange = sset.exchange, None
+            sset.d_all = torch.zeros((sset.num_global, capi.B2_LINEARIZED_DOUBLES), dtype=torch.float64, device=dev)
+            ref_all = sset.linearize_device().clone()
+            barrier()
+            sset.exchange = saved
+            got_all = sset.linearize_device().clone()
+            barrier()
+            assert torch.equal(ref_all, got_all), "peer-memory exchange and all-reduce disagree"
         n_inliers = int(rec[rank, 121])
         launches_dev = sset.set.launch_count() - launches0
         if world == 1:
@@ -388,7 +403,7 @@ def run_gpu(args):
                 "inliers": n_inliers,
                 "hit_rate": n_inliers / N_SOURCE,
                 "factors_per_gpu": 1,
-                "parallelism": f"factor-sharded x{world}" + (" + 1 all-reduce of [N x 128] f64" if world > 1 else ""),
+                "parallelism": f"factor-sharded x{world}" + (f"; records exchanged by {exchange_path}" if world > 1 else ""),
                 "source_storage": {"point_bytes": int(cinfo.point_bytes), "cov_bytes": int(cinfo.cov_bytes), "morton_ordered": bool(cinfo.reordered)},
                 "pose_perturbation": {"rot_rad": POSE_ROT, "trans_m": POSE_TRANS},
                 "l2": "flushed between timed steps (256 MiB write, then 256 MiB read so no dirty lines remain)" if not args.no_flush else "WARM (diagnostic run, not a valid number)",

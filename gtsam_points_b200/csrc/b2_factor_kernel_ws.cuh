@@ -133,10 +133,14 @@ __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
   // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
   if (sig.flag == nullptr) return;
   const unsigned int prev = atomicAdd(sig.counter, 1u);
-  if (prev == sig.total - 1u) {  // every factor of this host call is done: re-arm the counter, publish the sequence number
+  if (prev == sig.total - 1u) {  // every factor of this call is done: re-arm the counter, publish the sequence number
     *sig.counter = 0u;
     __threadfence_system();
-    *sig.flag = sig.seq;
+    if (sig.n_peers > 0) {
+      for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
+    } else {
+      *sig.flag = sig.seq;
+    }
   }
 }
 
@@ -201,6 +205,17 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
   }
   __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
   consumer_barrier();
+  if (sig.n_peers > 1) {
+    // multi-GPU exchange fused into the epilogue: copy the finished record into the same slot of every peer's buffer
+    // (plain stores to peer memory over NVLink), fence at system scope, then signal
+    for (int p = 0; p < sig.n_peers; p++) {
+      if (p == sig.my_rank) continue;
+      double* dst = sig.peer_out[p] + static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES;
+      for (int i = ctid; i < B2_LINEARIZED_DOUBLES; i += kCT) dst[i] = __ldcg(rec + i);
+    }
+    __threadfence_system();
+    consumer_barrier();
+  }
   if (ctid == 0) signal_done(sig);  // every writer of this record fenced before the barrier
   (void)kCT;
 }

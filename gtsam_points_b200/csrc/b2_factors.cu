@@ -38,6 +38,7 @@ namespace b2 {
 constexpr int kAcc = 32;  // accumulator slots per partial record (29 used)
 
 enum { MODE_LINEARIZE = 0, MODE_ERROR = 1 };
+constexpr int kMaxPeers = 8;  // GPUs of one NVSwitch node
 
 // Optional completion signal of a host call: the CTA that finishes the LAST factor of the call (device counter == total)
 // stores `seq` to a word in pinned, mapped host memory after the results (also mapped) have been fenced at system scope;
@@ -47,6 +48,14 @@ struct DoneSignal {
   volatile unsigned int* flag;
   unsigned int total;
   unsigned int seq;
+  // Multi-GPU exchange fused into the epilogue (b2_factor_set_linearize_exchange): besides its own buffer, the CTA that
+  // finishes a factor stores the 1 KiB record into the same slot of every peer GPU's buffer (NVLink peer stores), and the
+  // CTA that finishes the LAST local factor then raises flag[my_rank] = seq in every GPU's flag array (its own included).
+  // n_peers == 0: unused.  `flag` doubles as this GPU's own flag array in that mode.
+  int n_peers;
+  int my_rank;
+  double* peer_out[kMaxPeers];          // same offset as `out` of the launch, in each peer's buffer (entry my_rank unused)
+  unsigned int* peer_flag[kMaxPeers];   // each GPU's flag array [n_peers]
 };
 
 struct FactorDesc {
@@ -506,7 +515,7 @@ b2_status wait_done(b2_ctx* ctx, unsigned int seq) {
   return B2_OK;
 }
 
-b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{nullptr, nullptr, 0u, 0u}) {
+b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{}) {
   cudaStream_t st = s->ctx->stream;
   for (auto& g : s->groups) {
     g.fn[mode]<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, sig);
@@ -816,6 +825,55 @@ b2_status b2_factor_set_error_device(b2_factor_set* s, const double* d_deltas_ev
   return B2_OK;
 }
 
+b2_status b2_factor_set_linearize_exchange(b2_factor_set* s, const double* d_deltas, double* d_out, double* const* peer_out, unsigned int* const* peer_flags,
+                                           int n_peers, int my_rank, unsigned int seq) {
+  B2_REQUIRE(s && d_deltas && d_out && peer_out && peer_flags, "b2_factor_set_linearize_exchange: NULL argument");
+  B2_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && my_rank >= 0 && my_rank < n_peers, "b2_factor_set_linearize_exchange: bad peer count / rank");
+  B2_REQUIRE(seq != 0u, "b2_factor_set_linearize_exchange: seq must be non-zero");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  DoneSignal sig{};
+  sig.counter = s->ctx->d_done_counter;
+  sig.flag = peer_flags[my_rank];
+  sig.total = static_cast<unsigned int>(s->factors.size());
+  sig.seq = seq;
+  sig.n_peers = n_peers;
+  sig.my_rank = my_rank;
+  for (int p = 0; p < n_peers; p++) {
+    B2_REQUIRE(peer_flags[p] != nullptr && (p == my_rank || peer_out[p] != nullptr), "b2_factor_set_linearize_exchange: NULL peer pointer");
+    sig.peer_out[p] = peer_out[p];
+    sig.peer_flag[p] = peer_flags[p];
+  }
+  B2_TRY(launch_groups(s, MODE_LINEARIZE, d_deltas, d_deltas, d_out, sig));
+  for (auto* f : s->factors) f->linearized = true;
+  return B2_OK;
+}
+
+namespace {
+// Completes the exchange: returns (on the stream) once flags[r] == seq for every rank r, i.e. every GPU's records have
+// landed in this GPU's buffer.  One warp, lane r polls rank r's word; sleeps between polls, traps instead of hanging.
+__global__ void wait_flags_kernel(const volatile unsigned int* __restrict__ flags, int n, unsigned int seq) {
+  const int r = threadIdx.x;
+  if (r < n) {
+    unsigned polls = 0;
+    while (flags[r] != seq) {
+      __nanosleep(100);
+      if (++polls > (1u << 24)) __trap();
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+}  // namespace
+
+b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers, unsigned int seq) {
+  B2_REQUIRE(ctx && d_flags, "b2_exchange_wait: NULL argument");
+  B2_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers, "b2_exchange_wait: bad peer count");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_flags, n_peers, seq);
+  B2_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
 b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_linearized* out) {
   B2_REQUIRE(s && deltas && out, "b2_factor_set_linearize: NULL argument");
   static const bool trace = std::getenv("B2_TRACE") != nullptr;  // development aid: host-side time split of this call on stderr
@@ -838,7 +896,8 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
     t1 = std::chrono::steady_clock::now();
-    const DoneSignal sig{s->ctx->d_done_counter, s->ctx->d_done_flag, static_cast<unsigned int>(F), ++s->ctx->done_seq};
+    DoneSignal sig{};
+    sig.counter = s->ctx->d_done_counter, sig.flag = s->ctx->d_done_flag, sig.total = static_cast<unsigned int>(F), sig.seq = ++s->ctx->done_seq;
     B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig));
     t2 = std::chrono::steady_clock::now();
     B2_TRY(wait_done(s->ctx, sig.seq));
@@ -885,7 +944,8 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
     double* d_in = nullptr;
     B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_in), h, 0));
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
-    const DoneSignal sig{s->ctx->d_done_counter, s->ctx->d_done_flag, static_cast<unsigned int>(F), ++s->ctx->done_seq};
+    DoneSignal sig{};
+    sig.counter = s->ctx->d_done_counter, sig.flag = s->ctx->d_done_flag, sig.total = static_cast<unsigned int>(F), sig.seq = ++s->ctx->done_seq;
     B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res, sig));
     B2_TRY(wait_done(s->ctx, sig.seq));
   } else {

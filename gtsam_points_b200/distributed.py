@@ -79,11 +79,66 @@ class ShardedFactorSet:
         pin = self.device.type == "cuda"
         self.h_deltas = torch.zeros((F, 16), dtype=torch.float64, pin_memory=pin)
         self.h_all = torch.zeros((self.num_global, RECORD), dtype=torch.float64, pin_memory=pin)
+        self.exchange = None
+        self.step = 0
+        if self.compute is None and self.contiguous and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self._setup_peer_exchange()
+
+    # -- multi-GPU exchange fused into the kernel's epilogue (peer stores over NVLink instead of an NCCL all-reduce) -----
+    def _setup_peer_exchange(self):
+        """Symmetric (peer-mapped) result buffers: 2 x [num_global x 128] float64 (double-buffered by step parity) followed
+        by 2 x 8 uint32 flag words, identical layout on every rank.  torch's symmetric memory provides the allocation and
+        the exchange of peer pointers -- plumbing only; every byte is moved by this library's kernel.  Falls back to the
+        all-reduce path if symmetric memory is unavailable (B2_NO_PEER_EXCHANGE=1 forces that)."""
+        import os
+
+        if os.environ.get("B2_NO_PEER_EXCHANGE"):
+            return
+        torch, dist = self.torch, self.dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            if world > 8:
+                return
+            rec_doubles = self.num_global * RECORD
+            flag_doubles = 32  # 256 bytes: 2 parities x 8 flag words (uint32), padded
+            buf = symm_mem.empty(2 * rec_doubles + flag_doubles, dtype=torch.float64, device=self.device)
+            buf.zero_()
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # every rank zeroed its flags before anybody raises one
+            self.exchange = dict(buf=buf, hdl=hdl, ptrs=ptrs, world=world, rank=rank, rec_doubles=rec_doubles)
+        except Exception as e:  # pragma: no cover - depends on the driver / topology of the box
+            import warnings
+
+            warnings.warn(f"peer-memory exchange unavailable, using all-reduce: {e!r}")
+            self.exchange = None
+
+    def _linearize_exchange(self):
+        import ctypes as C
+
+        ex = self.exchange
+        self.step += 1
+        par = self.step & 1
+        world, rank, nrec = ex["world"], ex["rank"], ex["rec_doubles"]
+        out_off = (par * nrec + self.first * RECORD) * 8          # this rank's slots in the parity buffer (bytes)
+        flag_off = (2 * nrec) * 8 + par * 32                      # this parity's flag words (8 x uint32)
+        peer_out = (C.c_void_p * world)(*[p + out_off for p in ex["ptrs"]])
+        peer_flag = (C.c_void_p * world)(*[p + flag_off for p in ex["ptrs"]])
+        capi.check(capi.lib().b2_factor_set_linearize_exchange(self.set.h, self.d_deltas.data_ptr(), ex["ptrs"][rank] + out_off, peer_out, peer_flag, world, rank, self.step))
+        capi.check(capi.lib().b2_exchange_wait(self.ctx.h, ex["ptrs"][rank] + flag_off, world, self.step))
+        self.d_all = ex["buf"][par * nrec : (par + 1) * nrec].view(self.num_global, RECORD)
+        return self.d_all
 
     # -- device-resident step: poses already in self.d_deltas -----------------------------------------------------
     def linearize_device(self):
         """Local kernel launch(es) + ONE all-reduce; leaves all records in self.d_all (device).  Asynchronous."""
         torch, dist = self.torch, self.dist
+        if self.exchange is not None and self.local_factors:
+            return self._linearize_exchange()
         self.d_all.zero_()
         if self.local_factors:
             direct = self.compute is None and self.contiguous

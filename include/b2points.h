@@ -193,6 +193,17 @@ B2_API b2_status b2_factor_set_error(b2_factor_set* set, const double* deltas_ev
  * context's stream.  Asynchronous: no host synchronisation; ordering is the stream's. */
 B2_API b2_status b2_factor_set_linearize_device(b2_factor_set* set, const double* d_deltas, double* d_out);
 B2_API b2_status b2_factor_set_error_device(b2_factor_set* set, const double* d_deltas_eval, double* d_out_errors);
+/* Multi-GPU exchange fused into the kernel (one process per GPU, all GPUs of one NVLink / NVSwitch node): like
+ * b2_factor_set_linearize_device, and in the same launch the epilogue that finishes a factor also stores its record into
+ * the same slot of every peer GPU's result buffer (peer_out[p]: device pointer, valid on THIS device, to peer p's buffer at
+ * the offset that corresponds to d_out; entry my_rank is ignored), and the CTA that finishes the last local factor raises
+ * peer_flags[p][my_rank] = seq on every GPU p (own included).  b2_exchange_wait enqueues a wait, on the context's stream,
+ * until flags[r] == seq for all r < n_peers: after it this GPU's buffer holds every rank's records.  Replaces the single
+ * all-reduce of the [F x 128] block the reference would need; callers double-buffer by step parity.
+ * seq must be non-zero and change from step to step. */
+B2_API b2_status b2_factor_set_linearize_exchange(b2_factor_set* set, const double* d_deltas, double* d_out, double* const* peer_out,
+                                                  unsigned int* const* peer_flags, int n_peers, int my_rank, unsigned int seq);
+B2_API b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers, unsigned int seq);
 /* Number of kernel launches issued by this set since creation (for bench.py's gpu_launches). */
 B2_API uint64_t b2_factor_set_launch_count(const b2_factor_set* set);
 
