@@ -77,6 +77,7 @@ SIGNATURES = {
     "b2_factor_set_error_device": (C.c_int, [_vp, _vp, _vp]),
     "b2_factor_set_linearize_exchange": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),
     "b2_exchange_wait": (C.c_int, [_vp, _vp, C.c_int, C.c_uint]),
+    "b2_exchange_signal": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),
     "b2_factor_set_launch_count": (C.c_uint64, [_vp]),
 }
 

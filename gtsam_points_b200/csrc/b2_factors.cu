@@ -857,13 +857,40 @@ __global__ void wait_flags_kernel(const volatile unsigned int* __restrict__ flag
     unsigned polls = 0;
     while (flags[r] != seq) {
       __nanosleep(100);
-      if (++polls > (1u << 24)) __trap();
+      if (++polls > (1u << 28)) __trap();  // ~30 s: another rank may still be loading its modules at the first step
     }
   }
   __syncwarp();
   __threadfence_system();
 }
 }  // namespace
+
+namespace {
+// A rank that owns no factor still has to take part in the exchange: raise its flag on every GPU.
+__global__ void raise_flags_kernel(DoneSignal sig) {
+  if (threadIdx.x < sig.n_peers) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[threadIdx.x] + sig.my_rank) = sig.seq;
+  }
+}
+}  // namespace
+
+b2_status b2_exchange_signal(b2_ctx* ctx, unsigned int* const* peer_flags, int n_peers, int my_rank, unsigned int seq) {
+  B2_REQUIRE(ctx && peer_flags, "b2_exchange_signal: NULL argument");
+  B2_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && my_rank >= 0 && my_rank < n_peers && seq != 0u, "b2_exchange_signal: bad arguments");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  DoneSignal sig{};
+  sig.n_peers = n_peers;
+  sig.my_rank = my_rank;
+  sig.seq = seq;
+  for (int p = 0; p < n_peers; p++) {
+    B2_REQUIRE(peer_flags[p] != nullptr, "b2_exchange_signal: NULL peer pointer");
+    sig.peer_flag[p] = peer_flags[p];
+  }
+  raise_flags_kernel<<<1, 32, 0, ctx->stream>>>(sig);
+  B2_CUDA(cudaGetLastError());
+  return B2_OK;
+}
 
 b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers, unsigned int seq) {
   B2_REQUIRE(ctx && d_flags, "b2_exchange_wait: NULL argument");

@@ -81,8 +81,16 @@ class ShardedFactorSet:
         self.h_all = torch.zeros((self.num_global, RECORD), dtype=torch.float64, pin_memory=pin)
         self.exchange = None
         self.step = 0
-        if self.compute is None and self.contiguous and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            self._setup_peer_exchange()
+        if self.compute is None and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            # every rank must take the same transport: agree (one tiny collective at construction) that all of them can
+            eligible = torch.tensor([1 if (self.contiguous or not self.local_factors) else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(eligible, op=dist.ReduceOp.MIN, group=self.group)
+            if int(eligible.item()) == 1:
+                self._setup_peer_exchange()
+                ok = torch.tensor([1 if self.exchange is not None else 0], dtype=torch.int32, device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0:
+                    self.exchange = None
 
     # -- multi-GPU exchange fused into the kernel's epilogue (peer stores over NVLink instead of an NCCL all-reduce) -----
     def _setup_peer_exchange(self):
@@ -128,7 +136,10 @@ class ShardedFactorSet:
         flag_off = (2 * nrec) * 8 + par * 32                      # this parity's flag words (8 x uint32)
         peer_out = (C.c_void_p * world)(*[p + out_off for p in ex["ptrs"]])
         peer_flag = (C.c_void_p * world)(*[p + flag_off for p in ex["ptrs"]])
-        capi.check(capi.lib().b2_factor_set_linearize_exchange(self.set.h, self.d_deltas.data_ptr(), ex["ptrs"][rank] + out_off, peer_out, peer_flag, world, rank, self.step))
+        if self.local_factors:
+            capi.check(capi.lib().b2_factor_set_linearize_exchange(self.set.h, self.d_deltas.data_ptr(), ex["ptrs"][rank] + out_off, peer_out, peer_flag, world, rank, self.step))
+        else:  # nothing to linearize on this rank: still take part in the exchange
+            capi.check(capi.lib().b2_exchange_signal(self.ctx.h, peer_flag, world, rank, self.step))
         capi.check(capi.lib().b2_exchange_wait(self.ctx.h, ex["ptrs"][rank] + flag_off, world, self.step))
         self.d_all = ex["buf"][par * nrec : (par + 1) * nrec].view(self.num_global, RECORD)
         return self.d_all
@@ -137,7 +148,7 @@ class ShardedFactorSet:
     def linearize_device(self):
         """Local kernel launch(es) + ONE all-reduce; leaves all records in self.d_all (device).  Asynchronous."""
         torch, dist = self.torch, self.dist
-        if self.exchange is not None and self.local_factors:
+        if self.exchange is not None:
             return self._linearize_exchange()
         self.d_all.zero_()
         if self.local_factors:

@@ -204,6 +204,8 @@ B2_API b2_status b2_factor_set_error_device(b2_factor_set* set, const double* d_
 B2_API b2_status b2_factor_set_linearize_exchange(b2_factor_set* set, const double* d_deltas, double* d_out, double* const* peer_out,
                                                   unsigned int* const* peer_flags, int n_peers, int my_rank, unsigned int seq);
 B2_API b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers, unsigned int seq);
+/* For a rank that owns no factor in this step: only raises peer_flags[p][my_rank] = seq on every GPU (stream-ordered). */
+B2_API b2_status b2_exchange_signal(b2_ctx* ctx, unsigned int* const* peer_flags, int n_peers, int my_rank, unsigned int seq);
 /* Number of kernel launches issued by this set since creation (for bench.py's gpu_launches). */
 B2_API uint64_t b2_factor_set_launch_count(const b2_factor_set* set);
 
