@@ -2,28 +2,29 @@
 // Included by b2_factors.cu after the shared pieces (FactorDesc, accumulate_point, warp_reduce32, epilogue).
 //
 // Why warp specialisation.  One correspondence is the dependent chain
-//     coordinates -> rotate/floor/hash -> bucket group -> voxel id -> voxel record + source covariance -> ~175 FP64 ops
+//     coordinates -> rotate/floor/hash -> bucket group -> voxel id -> voxel record + source covariance -> ~155 FP64 ops
 // and the reduction needs 29 float64 accumulators per thread (58 registers) plus the pose.  A single-role kernel
-// therefore runs at 8 warps / SM and cannot hide three dependent memory round trips (round-1 measurement: 53.7 us per
+// therefore runs at 8 warps / SM and cannot hide three dependent memory round trips (round-1 first form: 53.7 us per
 // 1M points, FP64 pipe 24 % busy, 44 % of samples stalled on the scoreboard).  Here the CTA (one per SM, persistent)
 // is split with `setmaxnreg` into
-//   * kP PROBE warps with few registers: stream coordinates, rotate, floor, hash, probe the voxel table (or walk the
-//     kd-tree / re-read the frozen correspondence), store corr[], issue L2 prefetches for the voxel record and the
-//     covariance lines of every hit, and append the HITS ONLY -- compacted with a ballot -- as 32-byte items
-//     (R p, point index, target id) to a shared-memory ring;
-//   * kC ACCUMULATE warps with many registers: pop dense batches of 32 items, gather record + covariance (L2 hits
-//     thanks to the prefetch, issued one batch ahead of their use), do the float64 arithmetic, keep the accumulators
-//     in registers for the CTA's whole run of a factor.
-// Compaction removes the divergence waste of the fused form (38 % of the points of the bench workload have no voxel),
-// the probe chain is hidden by (kP / 4) independent warps per scheduler, and the FP64 pipe sees dense warps only.
+//   * kP PROBE warps with few registers: stream coordinates (L2-prefetched kPrefetchAhead tiles ahead), rotate, floor,
+//     hash, probe the voxel table (or walk the kd-tree / re-read the frozen correspondence), store corr[], start the voxel
+//     record and covariance lines of every hit towards L2, and append the HITS ONLY -- compacted with a ballot -- as
+//     32-byte items (R p, point index, target id) to a shared-memory ring;
+//   * kC ACCUMULATE warps with many registers: pop dense batches of 32 * kIPL items, gather record + covariance, do the
+//     float64 arithmetic, keep the accumulators in registers for the CTA's whole run of a factor.
+// Compaction removes the divergence waste of the fused form (15-40 % of the points of the bench poses have no voxel), the
+// search runs in cheap warps whose number is chosen per factor kind, and the FP64 pipe sees dense warps only.
 //
 // Determinism.  Every probe warp owns ONE ring (single producer, single consumer), tile -> probe warp assignment is
-// static, an accumulate warp drains its kP / kC rings in strict rotation in batches of exactly 32 consecutive items, and
-// all cross-warp / cross-CTA sums run in a fixed order: results are bit-reproducible run to run.
-// Liveness.  A probe warp blocks only when its own ring holds > cap - 32 items (then its consumer can pop a batch when
-// it reaches that ring) or at the end of a factor run until the consumer acknowledges; an accumulate warp waits on a ring
-// only while it holds < 32 items and is not finished, in which case its producer is not blocked.  Spins are bounded
-// (trap instead of hanging the GPU).
+// static, an accumulate warp drains its kP / kC rings in strict rotation in batches of consecutive items, and all
+// cross-warp / cross-CTA sums run in a fixed order: results are bit-reproducible run to run.
+// Liveness.  A probe warp blocks only when its own ring is full (then its consumer can pop a batch when the rotation
+// reaches that ring) or at the end of a factor run until the consumer acknowledges; an accumulate warp waits on a ring
+// only while it holds less than a batch and is not finished, in which case its producer is not blocked.  Waits sleep
+// between polls and are bounded (trap instead of hanging the GPU).
+// Measurement aids (never defined in the production build): B2_WS_TIMING (per-CTA timestamps), B2_WS_DEBUG_NO_PROBE /
+// B2_WS_DEBUG_NO_ACCUM (role isolation: results are garbage, timing only); see profiles/r01b_experiments.md.
 // This file is included once per kernel configuration (no include guard): the includer defines B2_WS_NAMESPACE and the
 // B2_WS_* parameters (see b2_factors.cu), e.g. few fat accumulate warps + many thin probe warps for the kd-tree path.
 
@@ -55,11 +56,6 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
-  return v;
 }
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v) : "memory");
