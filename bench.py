@@ -146,10 +146,12 @@ def cpu_threads(orc) -> int:
 
         phys = psutil.cpu_count(logical=False)
         if phys:
-            return max(1, min(int(phys), orc.max_threads()))
+            # not clamped by omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, and the oracle
+            # passes the count explicitly (`num_threads(n)` clause), which overrides that default
+            return max(1, min(int(phys), len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    return orc.max_threads()
+    return max(orc.max_threads(), 1)
 
 
 def time_cpu(tp, tc, sp, sc, poses, warmup: int, steps: int):
