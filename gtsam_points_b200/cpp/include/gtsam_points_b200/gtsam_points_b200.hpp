@@ -230,6 +230,11 @@ using LinearFactorPtr = std::shared_ptr<HessianFactor>;
 
 class NonlinearFactorSetGPU;
 
+// factors/integrated_gicp_factor.hpp:20-24.  The device path recomputes M = (C_B + R C_A R^T)^-1 from the rotation of the
+// linearization point inside the kernel (the reference's NONE behaviour, no cache to keep in HBM), so the mode is accepted
+// for source compatibility and has no effect on results beyond rounding.
+enum class FusedCovCacheMode { FULL, COMPACT, NONE };
+
 class IntegratedMatchingCostFactorB200 : public FactorBase {
 public:
   ~IntegratedMatchingCostFactorB200() override { b2_factor_destroy(factor_); }
@@ -335,6 +340,16 @@ public:
     init();
   }
   GaussianVoxelMapGPU::ConstPtr get_target() const { return target_voxels_; }
+  // integrated_vgicp_factor.hpp:71-90 -- kept for source compatibility: the device path has no thread knob and no cache
+  void set_num_threads(int) {}
+  void set_fused_cov_cache_mode(FusedCovCacheMode) {}
+  // NonlinearFactor::clone (integrated_vgicp_factor.hpp:90): a new factor over the same (shared) target map and source cloud
+  shared_ptr clone() const {
+    return is_binary_ ? std::make_shared<IntegratedVGICPFactor>(this->keys()[0], this->keys()[1], target_voxels_, source_)
+                      : std::make_shared<IntegratedVGICPFactor>(fixed_target_pose_, this->keys()[0], target_voxels_, source_);
+  }
+  // device bytes this factor owns itself (correspondence array + linearization point); clouds / maps are shared
+  std::size_t memory_usage() const { return b2_factor_num_points(factor_) * sizeof(std::int32_t) + 16 * sizeof(double) + sizeof(*this); }
 
 private:
   void init() {
@@ -369,8 +384,29 @@ public:
   : IntegratedMatchingCostFactorB200(fixed_target_pose, source_key), target_(target), source_(source), tree_(target_tree) {
     init();
   }
+  // the reference builds a KdTree2 over the target when no search tree is given (integrated_gicp_factor_impl.hpp:47-51);
+  // here that tree is built on the device
+  IntegratedGICPFactor(Key target_key, Key source_key, const PointCloudGPU::ConstPtr& target, const PointCloudGPU::ConstPtr& source, const double* target_points,
+                       int target_point_stride)
+  : IntegratedGICPFactor(target_key, source_key, target, source, std::make_shared<KdTreeGPU>(target_points, target_point_stride, target->size(), target->context())) {}
   void set_num_threads(int) {}  // kept for source compatibility; the device path has no thread knob
+  void set_fused_cov_cache_mode(FusedCovCacheMode) {}
   void set_max_correspondence_distance(double dist) { check(b2_factor_set_max_correspondence_distance(factor_, dist), "b2_factor_set_max_correspondence_distance"); }
+  // integrated_gicp_factor.hpp:103-109: the reference may SKIP re-association when the pose moved less than these
+  // tolerances since the last update (default 0 = always update).  The device path always re-associates (the search is
+  // fused into the linearization kernel and costs less than the skip would save), i.e. it behaves like tolerance 0; the
+  // values are kept so that callers can read them back.
+  void set_correspondence_update_tolerance(double angle, double trans) {
+    correspondence_update_tolerance_rot_ = angle;
+    correspondence_update_tolerance_trans_ = trans;
+  }
+  shared_ptr clone() const {
+    return is_binary_ ? std::make_shared<IntegratedGICPFactor>(this->keys()[0], this->keys()[1], target_, source_, tree_)
+                      : std::make_shared<IntegratedGICPFactor>(fixed_target_pose_, this->keys()[0], target_, source_, tree_);
+  }
+  std::size_t memory_usage() const {
+    return b2_factor_num_points(factor_) * sizeof(std::int32_t) + 16 * sizeof(double) + target_->size() * 10 * sizeof(double) + sizeof(*this);
+  }
 
 private:
   void init() {
@@ -382,6 +418,7 @@ private:
   }
   PointCloudGPU::ConstPtr target_, source_;
   KdTreeGPU::ConstPtr tree_;
+  double correspondence_update_tolerance_rot_ = 0.0, correspondence_update_tolerance_trans_ = 0.0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

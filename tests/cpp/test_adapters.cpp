@@ -47,6 +47,13 @@ int main(int argc, char** argv) {
 
   auto vgicp = std::make_shared<IntegratedVGICPFactor>(0, 1, voxels, source);
   auto gicp = std::make_shared<IntegratedGICPFactor>(0, 1, target, source, tree);
+  // the reference's tuning setters are accepted (source compatibility) and do not change results
+  vgicp->set_num_threads(4);
+  vgicp->set_fused_cov_cache_mode(FusedCovCacheMode::COMPACT);
+  gicp->set_num_threads(4);
+  gicp->set_fused_cov_cache_mode(FusedCovCacheMode::FULL);
+  gicp->set_correspondence_update_tolerance(0.0, 0.0);
+  if (vgicp->memory_usage() == 0 || gicp->memory_usage() == 0 || vgicp->get_target() != voxels) return 3;
 
   Values values, values2;
   Mat4 a, b, c;
