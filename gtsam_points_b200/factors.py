@@ -123,7 +123,16 @@ class IntegratedMatchingCostFactor:
         return out
 
     def memory_usage(self) -> int:
-        return 0
+        """Device bytes the factor owns itself (correspondence array + linearization point); clouds / maps are shared."""
+        return self.source.size() * 4 + 16 * 8
+
+    # -- tuning knobs of the reference, accepted for drop-in compatibility ------------------------------------------
+    def set_num_threads(self, n: int):
+        """The device path has no thread knob (integrated_vgicp_factor.hpp:71-73, integrated_gicp_factor.hpp:95-97)."""
+
+    def set_fused_cov_cache_mode(self, mode):
+        """The kernel recomputes (C_B + R C_A R^T)^-1 from the linearization rotation (the reference's NONE behaviour):
+        there is no cache to choose a layout for (integrated_gicp_factor.hpp:20-24, :106-109)."""
 
     def __del__(self):
         try:
@@ -152,6 +161,12 @@ class IntegratedVGICPFactor(IntegratedMatchingCostFactor):
     def get_target(self):
         return self.target_voxels
 
+    def clone(self):
+        """NonlinearFactor::clone (integrated_vgicp_factor.hpp:90): a new factor over the same (shared) map and cloud."""
+        a0 = self._keys[0] if self.is_binary else self.fixed_target_pose
+        a1 = self._keys[1] if self.is_binary else self._keys[0]
+        return IntegratedVGICPFactor(a0, a1, self.target_voxels, self.source, ctx=self.ctx)
+
 
 IntegratedVGICPFactorGPU = IntegratedVGICPFactor
 
@@ -176,8 +191,16 @@ class IntegratedGICPFactor(IntegratedMatchingCostFactor):
     def set_max_correspondence_distance(self, dist: float):
         capi.check(capi.lib().b2_factor_set_max_correspondence_distance(self.h, float(dist)))
 
-    def set_num_threads(self, n: int):  # kept for drop-in compatibility; the device path has no thread knob
-        pass
+    def set_correspondence_update_tolerance(self, angle: float, trans: float):
+        """integrated_gicp_factor.hpp:103-109: the reference may skip re-association when the pose moved less than these
+        tolerances (default 0 = always update).  The device path always re-associates -- the search is fused into the
+        linearization kernel -- i.e. it behaves like tolerance 0; the values are only stored."""
+        self.correspondence_update_tolerance = (float(angle), float(trans))
+
+    def clone(self):
+        a0 = self._keys[0] if self.is_binary else self.fixed_target_pose
+        a1 = self._keys[1] if self.is_binary else self._keys[0]
+        return IntegratedGICPFactor(a0, a1, self.target, self.source, target_tree=self.target_tree, ctx=self.ctx)
 
 
 class NonlinearFactorSetGPU:
