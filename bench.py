@@ -173,6 +173,21 @@ def time_cpu(tp, tc, sp, sc, poses, warmup: int, steps: int):
     return times, threads
 
 
+def time_cpu_single_thread(tp, tc, sp, sc, pose):
+    """The reference's DEFAULT is num_threads = 1 (factors/impl/integrated_gicp_factor_impl.hpp:29): one warm-up + one timed
+    linearize() of the same workload on one core, reported next to the all-cores number."""
+    import oracle_lib as orc
+
+    vm = orc.VoxelMap(RESOLUTION)
+    tgt = orc.Cloud(tp, tc)
+    vm.insert(tgt)
+    f = orc.Factor(vm, orc.Cloud(sp, sc), num_threads=1)
+    f.linearize_raw(pose)
+    t0 = time.perf_counter()
+    f.linearize_raw(pose)
+    return N_SOURCE / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -380,7 +395,8 @@ def run_gpu(args):
                 "unit": UNIT,
                 "cores": threads,
                 "kind": "port",
-                "sample": f"{cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, OMP threads = all host cores",
+                "sample": f"{cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, one OpenMP thread per physical core",
+                "single_thread_value": time_cpu_single_thread(tp, tc, sp, sc, poses[0]),  # the reference's default num_threads = 1
             }
         line = {
             "metric": METRIC,
