@@ -784,6 +784,105 @@ void orc_kdtree_knn(const orc_kdtree* t, const double* queries, size_t nq, int k
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// estimate_covariances (src/gtsam_points/features/covariance_estimation.cpp:18-77), EIG regularisation:
+//   k nearest neighbours of every point (the point itself included), cov = (sum p p^T - mean sum p^T) / k over the 4-vectors
+//   (top-left 3x3 used), C_i = V diag(eigen_values) V^-1 with V the eigenvectors of cov in ASCENDING eigenvalue order
+//   (SelfAdjointEigenSolver::computeDirect), fewer than k neighbours => identity.
+// Eigen is not available: the symmetric 3x3 eigen decomposition is restated with cyclic Jacobi rotations in float64 (the
+// eigenvectors of a symmetric matrix are unique up to sign when the eigenvalues are distinct, and V diag V^T does not
+// depend on the signs), so the result agrees with Eigen's closed-form solver to rounding wherever the spectrum is not
+// degenerate.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+void jacobi_eigen3(const double A_in[3][3], double w[3], double V[3][3]) {
+  double A[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      A[i][j] = A_in[i][j];
+      V[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 64; sweep++) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) {  // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {  // A <- J^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {  // V <- V J
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < 3; i++) w[i] = A[i][i];
+  std::sort(order, order + 3, [&](int a, int b) { return w[a] < w[b]; });
+  double ws[3], Vs[3][3];
+  for (int j = 0; j < 3; j++) {
+    ws[j] = w[order[j]];
+    for (int i = 0; i < 3; i++) Vs[i][j] = V[i][order[j]];
+  }
+  for (int j = 0; j < 3; j++) {
+    w[j] = ws[j];
+    for (int i = 0; i < 3; i++) V[i][j] = Vs[i][j];
+  }
+}
+}  // namespace
+
+void orc_estimate_covariances(const orc_cloud* cloud, int k_neighbors, const double* eigen_values3, int num_threads, double* out_cov3x3) {
+  const size_t n = orc_cloud_size(cloud);
+  orc_kdtree* tree = orc_kdtree_create(cloud, num_threads);  // covariance_estimation.cpp:19
+  if (num_threads < 1) num_threads = 1;
+#pragma omp parallel for num_threads(num_threads) schedule(guided, 8)
+  for (long i = 0; i < static_cast<long>(n); i++) {
+    std::vector<size_t> k_indices(k_neighbors);
+    std::vector<double> k_sq_dists(k_neighbors);
+    const Vec4& pi = cloud->points[i];
+    const double q[3] = {pi[0], pi[1], pi[2]};
+    const size_t found = tree->knn_search(q, k_neighbors, k_indices.data(), k_sq_dists.data(), std::numeric_limits<double>::max());
+    double* out = out_cov3x3 + static_cast<size_t>(i) * 9;
+    if (found < static_cast<size_t>(k_neighbors)) {  // :27-31 (warning + identity)
+      for (int a = 0; a < 9; a++) out[a] = (a % 4 == 0) ? 1.0 : 0.0;
+      continue;
+    }
+    double sum_p[3] = {0, 0, 0}, sum_c[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (size_t j = 0; j < found; j++) {  // :36-40
+      const Vec4& pt = cloud->points[k_indices[j]];
+      for (int a = 0; a < 3; a++) {
+        sum_p[a] += pt[a];
+        for (int b = 0; b < 3; b++) sum_c[a][b] += pt[a] * pt[b];
+      }
+    }
+    double cov[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) cov[a][b] = (sum_c[a][b] - (sum_p[a] / found) * sum_p[b]) / found;  // :42-43
+    double w[3], V[3][3];
+    jacobi_eigen3(cov, w, V);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {  // :49-53, V orthonormal => V^-1 = V^T
+        double v = 0.0;
+        for (int c = 0; c < 3; c++) v += V[a][c] * eigen_values3[c] * V[b][c];
+        out[a * 3 + b] = v;
+      }
+  }
+  orc_kdtree_destroy(tree);
+}
+
 orc_factor* orc_vgicp_create(const orc_voxelmap* target, const orc_cloud* source) {
   if (!source->has_covs()) {
     std::fprintf(stderr, "error: source don't have covs!!\n");  // vgicp_impl:37-40

@@ -66,6 +66,10 @@ void orc_kdtree_knn(const orc_kdtree*, const double* queries, size_t nq, int k, 
                     int32_t* out_found, int num_threads);
 size_t orc_kdtree_num_nodes(const orc_kdtree*);
 
+/* estimate_covariances with EIG regularisation (src/gtsam_points/features/covariance_estimation.cpp:18-77):
+ * out_cov3x3 = n x 9; eigen_values3 in ascending-eigenvalue order (reference default 1e-3, 1, 1). */
+void orc_estimate_covariances(const orc_cloud* cloud, int k_neighbors, const double* eigen_values3, int num_threads, double* out_cov3x3);
+
 /* IntegratedVGICPFactor_ / IntegratedGICPFactor_ in FusedCovCacheMode::FULL */
 orc_factor* orc_vgicp_create(const orc_voxelmap* target, const orc_cloud* source);
 orc_factor* orc_gicp_create(const orc_cloud* target, const orc_kdtree* tree, const orc_cloud* source);

@@ -93,3 +93,27 @@ def linearize(delta, src_pts, src_covs, mean_B, cov_B, corr, delta_eval=None):
         num_inliers=int(valid.sum()),
     )
     return out
+
+
+def estimate_covariances(pts, k=10, eig=(1e-3, 1.0, 1.0), chunk=1024):
+    """Brute-force float64 restatement of src/gtsam_points/features/covariance_estimation.cpp:18-77 (EIG regularisation):
+    k nearest neighbours incl. the point itself, cov = (sum p p^T - mean sum p^T) / k, eigenvalues replaced by `eig` in
+    ascending-eigenvalue order.  Also returns the eigenvalue gaps used to judge how well-defined each result is."""
+    n = len(pts)
+    covs = np.zeros((n, 3, 3))
+    gaps = np.zeros(n)
+    for s in range(0, n, chunk):
+        q = pts[s : s + chunk]
+        d = ((q[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+        idx = np.argpartition(d, k, axis=1)[:, :k]
+        nb = pts[idx]
+        sum_p = nb.sum(1)
+        sum_c = np.einsum("nki,nkj->nij", nb, nb)
+        mean = sum_p / k
+        c = (sum_c - mean[:, :, None] * sum_p[:, None, :]) / k
+        c = 0.5 * (c + c.transpose(0, 2, 1))
+        w, v = np.linalg.eigh(c)
+        covs[s : s + chunk] = np.einsum("nij,j,nkj->nik", v, np.array(eig), v)
+        gaps[s : s + chunk] = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300)
+    return 0.5 * (covs + covs.transpose(0, 2, 1)), gaps
+

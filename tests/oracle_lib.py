@@ -47,6 +47,7 @@ def lib():
         L.orc_kdtree_num_nodes.restype = C.c_size_t
         L.orc_kdtree_num_nodes.argtypes = [vp]
         L.orc_kdtree_knn.argtypes = [vp, dp, C.c_size_t, C.c_int, C.c_double, C.POINTER(C.c_uint64), dp, ip, C.c_int]
+        L.orc_estimate_covariances.argtypes = [vp, C.c_int, dp, C.c_int, dp]
         L.orc_vgicp_create.restype = vp
         L.orc_vgicp_create.argtypes = [vp, vp]
         L.orc_gicp_create.restype = vp
@@ -127,6 +128,15 @@ class VoxelMap:
         if getattr(self, "h", None):
             lib().orc_voxelmap_destroy(self.h)
             self.h = None
+
+
+def estimate_covariances(points, k_neighbors=10, eigen_values=(1e-3, 1.0, 1.0), num_threads=1):
+    """estimate_covariances(points, k, eigen_values, num_threads) of the reference (EIG regularisation) -> n x 3 x 3."""
+    cloud = Cloud(points)
+    out = np.zeros((len(points), 3, 3))
+    ev = np.ascontiguousarray(eigen_values, dtype=np.float64)
+    lib().orc_estimate_covariances(cloud.h, int(k_neighbors), _dp(ev), int(num_threads), _dp(out))
+    return out
 
 
 class KdTree:

@@ -107,3 +107,23 @@ def test_calc_delta():
     rng = np.random.default_rng(3)
     Tt, Ts = syn.random_pose(rng, 1.0, 10.0), syn.random_pose(rng, 1.0, 10.0)
     assert np.abs(orc.calc_delta(Tt, Ts) - np.linalg.inv(Tt) @ Ts).max() < 1e-12
+
+
+def test_covariance_estimation_matches_numpy():
+    """Oracle restatement of estimate_covariances (next widening step) vs brute-force numpy + eigh.
+    With eigenvalues (eps, 1, 1) the result is I - (1 - eps) n n^T, n = eigenvector of the smallest eigenvalue: it is
+    well-defined where the two smallest eigenvalues are separated, and compared only there."""
+    pts, _ = syn.make_cloud(6000, stream=5, scale=0.1)
+    got = orc.estimate_covariances(pts, 10, (1e-3, 1.0, 1.0), num_threads=4)
+    ref, gaps = np_ref.estimate_covariances(pts, 10)
+    ok = gaps > 1e-3
+    assert ok.mean() > 0.9
+    assert np.abs(got[ok] - ref[ok]).max() < 1e-6
+    assert np.allclose(got, got.transpose(0, 2, 1), atol=1e-12)
+    # every result has the prescribed spectrum whatever the neighbourhood looked like
+    w = np.linalg.eigvalsh(got)
+    assert np.abs(w - np.array([1e-3, 1.0, 1.0])).max() < 1e-9
+    # different regularisation, single thread
+    got2 = orc.estimate_covariances(pts[:500], 5, (1e-2, 0.5, 2.0), num_threads=1)
+    assert np.abs(np.linalg.eigvalsh(got2) - np.array([1e-2, 0.5, 2.0])).max() < 1e-9
+
