@@ -47,7 +47,7 @@ static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 * kIPL + kWarpPoints
 static_assert(kWarpPoints * 4 % 128 == 0 || kPPL == 1, "coordinate prefetch works on whole lines");
 constexpr size_t kRingBytes = static_cast<size_t>(kP) * 2 * kRing * sizeof(double2);
 
-constexpr unsigned kSpinLimit = 1u << 22;  // polls (with sleeps: seconds) before a wait traps: a protocol bug must not hang the GPU
+constexpr unsigned kSpinLimit = 1u << 25;  // polls (with sleeps: >= 2 s, typically tens of seconds) before a wait traps: a protocol bug must not hang the GPU
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
   uint32_t v;
