@@ -48,6 +48,46 @@ UNIT = "correspondences/s"
 WORKLOAD = "IntegratedVGICPFactor: 1M-pt source into 0.5 m GaussianVoxelMap (1M-pt target), one linearize() per step"
 
 
+def workload_config():
+    """`config` is IDENTICAL in both arms (the driver compares them); arm-specific facts go into `detail`."""
+    return {
+        "workload": WORKLOAD,
+        "n_source": N_SOURCE,
+        "n_target": N_TARGET,
+        "resolution": RESOLUTION,
+        "pose_perturbation": {"rot_rad": POSE_ROT, "trans_m": POSE_TRANS},
+        "l2": "flushed between timed steps (GPU arm: 256 MiB write then 256 MiB read; CPU arm: working set 320 MB >> LLC)",
+    }
+
+
+AFFINITY = sorted(os.sched_getaffinity(0))  # taken at import: once libgomp binds the main thread, sched_getaffinity(0) shrinks to its place
+
+
+def pin_openmp_env():
+    """the CPU arm runs thread-pinned.  libgomp reads these when it is first loaded, so they are set before
+    torch / the oracle are imported.  (Explicit user settings win.)"""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def host_info():
+    info = {"nproc": os.cpu_count(), "affinity": len(AFFINITY), "omp_proc_bind": os.environ.get("OMP_PROC_BIND"), "omp_places": os.environ.get("OMP_PLACES")}
+    try:
+        import psutil
+
+        info["physical_cores"] = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["cpu"] = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return info
+
+
 def make_inputs(rank: int):
     from gtsam_points_b200 import synthetic as syn
 
@@ -148,7 +188,7 @@ def cpu_threads(orc) -> int:
         if phys:
             # not clamped by omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, and the oracle
             # passes the count explicitly (`num_threads(n)` clause), which overrides that default
-            return max(1, min(int(phys), len(os.sched_getaffinity(0))))
+            return max(1, min(int(phys), len(AFFINITY)))
     except Exception:
         pass
     return max(orc.max_threads(), 1)
@@ -173,6 +213,23 @@ def time_cpu(tp, tc, sp, sc, poses, warmup: int, steps: int):
     return times, threads
 
 
+def cpu_value(times) -> float:
+    """correspondences/s from the MEDIAN call (median of >= 10 linearize() calls after warm-up)."""
+    return N_SOURCE / float(np.median(times))
+
+
+def time_cpu_native(steps: int, warmup: int):
+    """Same oracle compiled with -march=native ON THIS HOST (the reference's BUILD_WITH_MARCH_NATIVE option, off by default):
+    run in a child process because the library handle is process-global.  Returns correspondences/s or None."""
+    env = dict(os.environ, B2_ORACLE_NATIVE="1")
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup), "--no-native"],
+                             env=env, capture_output=True, text=True, timeout=600, preexec_fn=lambda: os.sched_setaffinity(0, AFFINITY))
+        return float(json.loads(out.stdout.strip().splitlines()[-1])["value"])
+    except Exception:
+        return None
+
+
 def time_cpu_single_thread(tp, tc, sp, sc, pose):
     """The reference's DEFAULT is num_threads = 1 (factors/impl/integrated_gicp_factor_impl.hpp:29): one warm-up + one timed
     linearize() of the same workload on one core, reported next to the all-cores number."""
@@ -193,27 +250,33 @@ def run_reference(args):
     if rank != 0:
         return  # the CPU arm runs on rank 0 only
     tp, tc, sp, sc = make_inputs(0)
-    poses = make_poses(0, args.steps + args.warmup)
-    times, threads = time_cpu(tp, tc, sp, sc, poses, args.warmup, args.steps)
-    total = float(np.sum(times))
-    value = N_SOURCE * args.steps / total
-    sample = f"{args.steps} linearize() calls of the full 1M-pt workload after {args.warmup} warm-up"
+    steps = max(args.steps, 10)  # median of >= 10 calls
+    poses = make_poses(0, steps + args.warmup)
+    times, threads = time_cpu(tp, tc, sp, sc, poses, args.warmup, steps)
+    value = cpu_value(times)
+    native = os.environ.get("B2_ORACLE_NATIVE") == "1"
+    sample = (f"median of {steps} linearize() calls of the full 1M-pt workload after {args.warmup} warm-up, one pinned OpenMP thread per physical core"
+              + (", -march=native build" if native else ", reference default flags (-O3, no -march=native)"))
+    cpu_baseline = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "min_ms": 1e3 * float(np.min(times)), "max_ms": 1e3 * float(np.max(times))}
+    if not native and not args.no_native:
+        cpu_baseline["native_value"] = time_cpu_native(steps, args.warmup)
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
-        "steps": args.steps,
+        "steps": steps,
         "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps,
+        "ms_per_step": 1e3 * float(np.median(times)),
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_source": N_SOURCE, "n_target": N_TARGET, "resolution": RESOLUTION, "threads": threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(),
+        "detail": {"threads": threads, "host": host_info()},
+        "cpu_baseline": cpu_baseline,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -272,6 +335,12 @@ def run_gpu(args):
             flush_r.sum()
         d_poses = torch.as_tensor(poses.reshape(K + W, 16), device=dev)
         launches0 = sset.set.launch_count()
+        import ctypes as C
+
+        dp = C.POINTER(C.c_double)
+        poses_c = [np.ascontiguousarray(p.reshape(1, 16)) for p in poses]
+        poses_p = [p.ctypes.data_as(dp) for p in poses_c]  # argument marshalling is not part of any measured call
+        issue_linearize = capi.lib().b2_factor_set_issue_linearize
 
         def barrier():
             if world > 1:
@@ -282,6 +351,8 @@ def run_gpu(args):
         for i in range(W):
             sset.d_deltas.copy_(d_poses[i : i + 1])
             sset.linearize_device()
+            if world == 1:
+                capi.check(issue_linearize(sset.set.h, poses_p[i], sset.d_all.data_ptr()))
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -296,8 +367,9 @@ def run_gpu(args):
                 barrier()  # ranks enter the timed step together: the collective must not absorb another rank's L2 flush
             ev[i][0].record(stream)
             if world == 1:
-                # single GPU: the step IS the kernel launch (no collective); the same events serve the roofline
-                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_all.data_ptr()))
+                # single GPU: the step IS the kernel launch (no collective); the same events serve the roofline.  The asynchronous
+                # entry point (NonlinearFactorGPU's issue_linearize): host pose in (by value with the launch), record left on the device
+                capi.check(issue_linearize(sset.set.h, poses_p[W + i], sset.d_all.data_ptr()))
             else:
                 sset.linearize_device()  # zero, kernel (records written in place), ONE all-reduce
             ev[i][1].record(stream)
@@ -334,10 +406,7 @@ def run_gpu(args):
         # ---- end-to-end arm: the public host entry point with HOST buffers (poses in, H/b records out) ----
         # N = 1: the C-ABI call itself (b2_factor_set_linearize), which is what NonlinearFactorSetGPU.linearize and the C++
         #        adapters issue; N > 1: ShardedFactorSet.linearize (host poses -> kernel -> all-reduce -> host records).
-        import ctypes as C
-
         h_out = np.zeros((1, capi.B2_LINEARIZED_DOUBLES))
-        dp = C.POINTER(C.c_double)
 
         linearize_host = capi.lib().b2_factor_set_linearize
         h_out_p = h_out.ctypes.data_as(dp)
@@ -348,8 +417,6 @@ def run_gpu(args):
                 return h_out
             return sset.linearize(pose)
 
-        poses_c = [np.ascontiguousarray(p.reshape(1, 16)) for p in poses]
-        poses_p = [p.ctypes.data_as(dp) for p in poses_c]  # argument marshalling is not part of the measured call
         for i in range(W):
             e2e_step(poses_c[i], poses_p[i])
         barrier()
@@ -388,14 +455,18 @@ def run_gpu(args):
         achieved = alg_bytes / (kern_ms_mean * 1e-3) / 1e9
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cs, cw = 3, 1
+            cs, cw = 10, 2
             times, threads = time_cpu(tp, tc, sp, sc, poses, cw, cs)
             cpu_baseline = {
-                "value": N_SOURCE * cs / float(np.sum(times)),
+                "value": cpu_value(times),
                 "unit": UNIT,
                 "cores": threads,
                 "kind": "port",
-                "sample": f"{cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, one OpenMP thread per physical core",
+                "sample": f"median of {cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, one pinned OpenMP thread per physical core, reference default flags",
+                "min_ms": 1e3 * float(np.min(times)),
+                "max_ms": 1e3 * float(np.max(times)),
+                "native_value": time_cpu_native(cs, cw),  # same code, -march=native (the reference's optional BUILD_WITH_MARCH_NATIVE)
+                "host": host_info(),
                 "single_thread_value": time_cpu_single_thread(tp, tc, sp, sc, poses[0]),  # the reference's default num_threads = 1
             }
         line = {
@@ -411,11 +482,8 @@ def run_gpu(args):
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD,
-                "n_source": N_SOURCE,
-                "n_target": N_TARGET,
-                "resolution": RESOLUTION,
+            "config": workload_config(),
+            "detail": {
                 "num_voxels": V,
                 "num_buckets": NB,
                 "inliers": n_inliers,
@@ -423,8 +491,7 @@ def run_gpu(args):
                 "factors_per_gpu": 1,
                 "parallelism": f"factor-sharded x{world}" + (f"; records exchanged by {exchange_path}" if world > 1 else ""),
                 "source_storage": {"point_bytes": int(cinfo.point_bytes), "cov_bytes": int(cinfo.cov_bytes), "morton_ordered": bool(cinfo.reordered)},
-                "pose_perturbation": {"rot_rad": POSE_ROT, "trans_m": POSE_TRANS},
-                "l2": "flushed between timed steps (256 MiB write, then 256 MiB read so no dirty lines remain)" if not args.no_flush else "WARM (diagnostic run, not a valid number)",
+                "l2_flush": not args.no_flush,
                 "setup_s": setup_s,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * 1, "d2h_bytes_per_step": 1024 * world, "ms_per_step": e2e_ms / K},
@@ -457,10 +524,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-native", action="store_true", help="reference arm: skip the secondary -march=native measurement")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps (NOT a valid bench number)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    pin_openmp_env()
     if args.impl == "reference":
         run_reference(args)
     else:

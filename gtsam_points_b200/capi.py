@@ -75,6 +75,11 @@ SIGNATURES = {
     "b2_factor_set_error": (C.c_int, [_vp, _dp, _dp]),
     "b2_factor_set_linearize_device": (C.c_int, [_vp, _vp, _vp]),
     "b2_factor_set_error_device": (C.c_int, [_vp, _vp, _vp]),
+    "b2_factor_set_issue_linearize": (C.c_int, [_vp, _dp, _vp]),
+    "b2_factor_set_issue_error": (C.c_int, [_vp, _dp, _vp]),
+    "b2_factor_set_sync": (C.c_int, [_vp]),
+    "b2_factor_set_store_linearized": (C.c_int, [_vp, _dp]),
+    "b2_factor_set_store_errors": (C.c_int, [_vp, _dp]),
     "b2_factor_set_linearize_exchange": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),
     "b2_exchange_wait": (C.c_int, [_vp, _vp, C.c_int, C.c_uint]),
     "b2_exchange_signal": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),

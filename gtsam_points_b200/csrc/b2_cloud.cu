@@ -175,6 +175,13 @@ b2_status b2_cloud_create(b2_ctx* ctx, const double* points, int point_stride, c
   c->ctx = ctx;
   c->n = n;
   c->n_pad = round_up(n > 0 ? n : 1, 32);
+  // every early return below (B2_CUDA included) releases the half-built cloud; disarmed right before success
+  struct Guard {
+    b2_cloud* c;
+    ~Guard() {
+      if (c) b2_cloud_destroy(c);
+    }
+  } guard{c};
 
   DevBuf raw_p, raw_c, d_res, d_keys, d_keys2, d_idx, d_tmp;
   if (n > 0) {
@@ -202,7 +209,6 @@ b2_status b2_cloud_create(b2_ctx* ctx, const double* points, int point_stride, c
     B2_CUDA(cudaMemcpyAsync(&h_res, d_res.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     if (h_res.flags & 4u) {
-      delete c;
       return fail(B2_ERR_INVALID_ARGUMENT, "b2_cloud_create: non-finite coordinate or covariance entry");
     }
   }
@@ -213,10 +219,7 @@ b2_status b2_cloud_create(b2_ctx* ctx, const double* points, int point_stride, c
   c->cov_bytes = covs ? (force64 ? 8 : (compact || !(h_res.flags & 2u)) ? 4 : 8) : 0;
   c->reordered = !(flags & B2_CLOUD_NO_REORDER) && n > 1;
 
-  auto cleanup_fail = [&](b2_status s) {
-    b2_cloud_destroy(c);
-    return s;
-  };
+  auto cleanup_fail = [&](b2_status s) { return s; };  // the guard above releases the cloud
 
   // Morton permutation
   if (c->reordered) {
@@ -268,6 +271,7 @@ b2_status b2_cloud_create(b2_ctx* ctx, const double* points, int point_stride, c
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cleanup_fail(fail(B2_ERR_CUDA, "b2_cloud_create: %s", cudaGetErrorString(e)));
   }
 
+  guard.c = nullptr;
   *out = c;
   return B2_OK;
 }

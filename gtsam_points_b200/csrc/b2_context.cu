@@ -25,20 +25,24 @@ b2_status fail(b2_status st, const char* fmt, ...) {
 }  // namespace b2
 
 b2_status b2_ctx::ensure_stage(size_t host_bytes, size_t dev_bytes) {
+  // the new buffer is allocated BEFORE the old one is released: a failed allocation leaves the context usable
   if (host_bytes > h_stage_bytes) {
-    if (h_stage) cudaFreeHost(h_stage);
-    h_stage = nullptr;
-    h_stage_bytes = 0;
     const size_t want = b2::round_up(host_bytes * 2, 4096);
-    B2_CUDA(cudaHostAlloc(&h_stage, want, cudaHostAllocMapped | cudaHostAllocPortable));
+    void* fresh = nullptr;
+    B2_CUDA(cudaHostAlloc(&fresh, want, cudaHostAllocMapped | cudaHostAllocPortable));
+    if (h_stage) {
+      cudaStreamSynchronize(stream);  // nothing in flight may still read the old staging area
+      cudaFreeHost(h_stage);
+    }
+    h_stage = fresh;
     h_stage_bytes = want;
   }
   if (dev_bytes > d_stage_bytes) {
-    if (d_stage) cudaFree(d_stage);
-    d_stage = nullptr;
-    d_stage_bytes = 0;
     const size_t want = b2::round_up(dev_bytes * 2, 4096);
-    B2_CUDA(cudaMalloc(&d_stage, want));
+    void* fresh = nullptr;
+    B2_CUDA(cudaMalloc(&fresh, want));
+    if (d_stage) cudaFree(d_stage);
+    d_stage = fresh;
     d_stage_bytes = want;
   }
   return B2_OK;

@@ -1,0 +1,715 @@
+// b2_factor_kernel_v2.cuh -- the hot kernel, second form: warp-specialised, every global stream staged asynchronously.
+// Included by b2_factors.cu after the shared pieces (FactorDesc, accumulate arithmetic, warp_reduce32, epilogue).
+//
+// Round-1's kernel (b2_factor_kernel_ws.cuh, still used by the kd-tree path) was latency bound: 16 warps per SM, each a
+// long dependent chain with its global loads on the scoreboard (probe warps: 48 % long-scoreboard stalls on the streamed
+// coordinates and the bucket group; accumulate warps: 11 gathers in front of every batch).  This form takes every byte
+// that CAN be known ahead of time off the scoreboards:
+//   * the STREAMS (3 coordinate planes, 6 covariance planes, the frozen correspondences in error mode: 94 % of the bytes)
+//     arrive through the TMA unit: per probe warp, one elected lane issues 1-D bulk copies (cp.async.bulk, 256-512 B per
+//     plane and 64-point warp tile) into a small multi-stage shared-memory ring, completion on an mbarrier
+//     (complete_tx::bytes).  Coordinates are staged kSX - 1 tiles ahead, covariances kLC tiles ahead and RETAINED until
+//     the accumulate warp has consumed every hit of the tile (it reads the covariance of a hit from the stage by its
+//     tile-local index -- hits travel through the ring as 32-byte items (R p, stage slot, target id) as before).
+//   * the GATHERED target records (80 B per hit) are fetched by the accumulate warp for batch k + 1 with cp.async
+//     (LDGSTS, 5 x 16 B per lane) into a private double buffer while it computes batch k: the float64 arithmetic reads
+//     nothing but shared memory.
+//   * the pose of single-factor launches is a by-value kernel parameter: DMUL / DFMA take it as constant-bank operands
+//     (no registers, no shared-memory reads), and the kernel never touches host memory on its way in.
+// What stays on a scoreboard is the bucket group of the hash probe (data dependent address), 2 points per lane in flight.
+//
+// Stage retention and liveness.  A covariance stage is re-armed only after the accumulate warp's published `head` has
+// passed the last hit of the tile that used it (`tile_end`).  Because the accumulate warp takes batches of exactly 32
+// consecutive hits, it could be waiting for hits that the probe warp cannot produce before the stage is free; in that case
+// (decided from hit counts alone, hence deterministic) the probe warp publishes a FORCED batch boundary `flush` = its
+// current tail: the accumulate warp then takes the shorter batch [head, flush).  Batch boundaries therefore depend only on
+// the data, never on timing: results stay bit-reproducible run to run.
+// Everything else (ring protocol, done / ack hand-shake per factor run, strict rotation, slot-ordered cross-CTA sums) is
+// the round-1 protocol.
+//
+// This file is included once per kernel configuration (no include guard); the includer defines B2_V2_NAMESPACE and the
+// B2_V2_* parameters (see b2_factors.cu).
+
+namespace b2 {
+namespace B2_V2_NAMESPACE {
+
+constexpr int kP = B2_V2_PRODUCERS;
+constexpr int kC = B2_V2_CONSUMERS;
+constexpr int kThreads = (kP + kC) * 32;
+constexpr int kPPL = B2_V2_PPL;          // points per probe lane and warp tile (independent chains interleaved for ILP)
+constexpr int kWarpPoints = 32 * kPPL;   // contiguous source points per probe warp and tile
+constexpr int kTile = kP * kWarpPoints;  // source points per CTA tile
+constexpr int kRing = B2_V2_RING;        // items per ring (power of two)
+constexpr int kSX = B2_V2_XYZ_STAGES;    // coordinate stages per probe warp (lookahead kSX - 1 tiles)
+constexpr int kSC = B2_V2_COV_STAGES;    // covariance stages per probe warp
+constexpr int kLC = B2_V2_COV_AHEAD;     // covariance lookahead in tiles (retention = kSC - kLC tiles after the tile is probed)
+constexpr int kRingsPerConsumer = kP / kC;
+constexpr uint32_t kBatch = 32u;
+static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
+static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 + kWarpPoints, "ring capacity: a tile's hits + a batch being read + a batch");
+static_assert(kSX >= 2 && kLC >= 1 && kSC > kLC, "stage counts");
+
+constexpr unsigned kSpinLimit = 1u << 25;  // polls (with sleeps: >= 2 s) before a wait traps: a protocol bug must not hang the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+struct Backoff {
+  unsigned ns, max_ns, polls;
+  __device__ __forceinline__ explicit Backoff(unsigned first_ns, unsigned cap_ns) : ns(first_ns), max_ns(cap_ns), polls(0u) {}
+  __device__ __forceinline__ void wait() {
+    __nanosleep(ns);
+    if (ns < max_ns) ns *= 2u;
+    if (++polls > kSpinLimit) __trap();
+  }
+};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kC * 32) : "memory"); }
+
+// ---- mbarrier / bulk-copy (TMA) / cp.async primitives ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned polls = 0;
+  while (!mbar_try_wait(bar, parity)) {  // try_wait suspends in hardware up to a time limit: no explicit sleep needed
+    if (++polls > (1u << 22)) __trap();
+  }
+}
+// global -> shared bulk copy (SASS: UBLKCP), `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- shared-memory layout ---------------------------------------------------------------------------------------------
+// dynamic part, per probe warp: [kSX coordinate stages | kSC covariance stages | ring], then per accumulate warp the
+// record double buffer.  Everything is a multiple of 128 bytes.
+constexpr uint32_t kRecBufBytes = 32u * kRecordDoubles * 8u;  // one batch of gathered target records
+template <typename PT, int MODE>
+struct XyzStage {
+  static constexpr uint32_t kPlane = kWarpPoints * sizeof(PT);
+  static constexpr uint32_t kCorrOff = 3u * kPlane;
+  static constexpr uint32_t kBytes = 3u * kPlane + (MODE == MODE_ERROR ? kWarpPoints * 4u : 0u);
+};
+template <typename CT>
+struct CovStage {
+  static constexpr uint32_t kPlane = kWarpPoints * sizeof(CT);
+  static constexpr uint32_t kBytes = 6u * kPlane;
+};
+constexpr uint32_t kRingBytes1 = 2u * kRing * 16u;
+template <typename PT, typename CT, int MODE>
+struct Layout {
+  static constexpr uint32_t kXyzOff = 0u;
+  static constexpr uint32_t kCovOff = kSX * XyzStage<PT, MODE>::kBytes;
+  static constexpr uint32_t kRingOff = kCovOff + kSC * CovStage<CT>::kBytes;
+  static constexpr uint32_t kWarpBytes = kRingOff + kRingBytes1;
+  static constexpr uint32_t kRecOff = kP * kWarpBytes;
+  static constexpr uint32_t kTotal = kRecOff + kC * 2u * kRecBufBytes;
+  static_assert(kWarpBytes % 128u == 0u, "stage alignment");
+};
+
+struct Shared {
+  FactorDesc desc;  // accumulate-side copy of the current factor's descriptor (flush / epilogue)
+  double red[kC][kAcc];
+  double tot[kAcc];
+  double A[36], X[36], D[36];
+  double R[9], t[3];  // pose the residuals of the current factor run are evaluated at (accumulate side)
+  double RL[9];       // rotation of its linearization point (== R when linearizing)
+  int flag;
+  // ring control words, one set per probe warp (all monotonic counters)
+  uint32_t tail[kP];   // items published by the probe warp
+  uint32_t head[kP];   // items consumed (operands read) by the accumulate warp
+  uint32_t done[kP];   // factor runs completed by the probe warp (tail is final for run e once done == e + 1)
+  uint32_t ack[kP];    // factor runs the accumulate warp has finished draining
+  uint32_t flush[kP];  // forced batch boundary (a tail value): the accumulate warp may take the short batch [head, flush)
+  uint32_t tile_end[kP][kSC];  // tail after the tile that last used covariance stage s
+  double probe_pose[kP][12];   // per probe warp: R (9, row-major) | t (3) of the factor run it is working on (multi-factor launches)
+  alignas(8) uint64_t bar_x[kP][kSX];
+  alignas(8) uint64_t bar_c[kP][kSC];
+};
+
+// tiles of CTA c: [c * T / G, (c + 1) * T / G) -- contiguous and balanced; the host uses the same formula for the slots
+__host__ __device__ __forceinline__ uint32_t cta_tile_begin(uint32_t c, uint32_t T, uint32_t G) {
+  return static_cast<uint32_t>(static_cast<unsigned long long>(c) * T / G);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-factor flush by the accumulate warps: warp butterfly -> cross-warp sum -> fixed slot; the last CTA of the
+// factor sums the slots in slot order and runs the epilogue (H_t = X^T A' X, ...).
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int ctid, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
+                                             const double* __restrict__ pose_lin, const DoneSignal& sig) {
+  constexpr int kCT = kC * 32;
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const double w = warp_reduce32(v, lane);
+  sh.red[warp][lane] = w;
+  consumer_barrier();
+  const FactorDesc& d = sh.desc;
+  const uint32_t slot = blockIdx.x - d.cta_first[MODE];
+  bool last;
+  if (d.num_slots[MODE] == 1u) {
+    // the whole factor lived in this CTA (small factors of a big set): no slot round trip through global memory
+    last = true;
+    if (ctid < kAcc) {
+      double s = sh.red[0][ctid];
+#pragma unroll
+      for (int k = 1; k < kC; k++) s += sh.red[k][ctid];
+      sh.tot[ctid] = s;
+    }
+    consumer_barrier();
+  } else {
+    if (warp == 0) {
+      double s = sh.red[0][lane];
+#pragma unroll
+      for (int k = 1; k < kC; k++) s += sh.red[k][lane];
+      partials[(static_cast<size_t>(d.slot_begin[MODE]) + slot) * kAcc + lane] = s;
+      __threadfence();  // only the writing warp pays for the fence
+    }
+    consumer_barrier();
+    if (ctid == 0) {
+      const unsigned int prev = atomicAdd(&counters[d.out_index], 1u);
+      sh.flag = (prev == d.num_slots[MODE] - 1u) ? 1 : 0;
+    }
+    consumer_barrier();
+    last = sh.flag != 0;
+    if (!last) return;
+    // ---- last CTA of this factor ----
+    __threadfence();
+    {
+      double s = 0.0;
+      for (uint32_t sl = warp; sl < d.num_slots[MODE]; sl += kC) s += __ldcg(&partials[(static_cast<size_t>(d.slot_begin[MODE]) + sl) * kAcc + lane]);
+      sh.red[warp][lane] = s;
+    }
+    consumer_barrier();
+    if (ctid < kAcc) {
+      double s = sh.red[0][ctid];
+#pragma unroll
+      for (int k = 1; k < kC; k++) s += sh.red[k][ctid];
+      sh.tot[ctid] = s;
+    }
+    if (ctid == 0) counters[d.out_index] = 0u;  // re-arm for the next launch
+    consumer_barrier();
+  }
+
+  if (MODE == MODE_ERROR) {
+    if (ctid == 0) {
+      out[d.out_index] = sh.tot[27];
+      __threadfence_system();  // `out` may be mapped host memory
+      signal_done(sig);
+    }
+    consumer_barrier();
+    return;
+  }
+  epilogue_build(sh.A, sh.X, sh.D, sh.tot, sh.R, sh.t, ctid);
+  consumer_barrier();
+  double* rec = out + static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES;
+  epilogue_store(rec, sh.A, sh.X, sh.D, sh.tot, ctid);
+  if (ctid >= 100 && ctid < 116) {
+    // remember the linearization point with the factor (error-only launches of ANY set read it back)
+    d.lin_pose[ctid - 100] = pose_lin[ctid - 100];
+  }
+  if (sig.n_peers > 1) {
+    // multi-GPU exchange fused into the epilogue: the finished record goes into the same slot of every peer's buffer.
+    // All peers' stores are issued before the single system-scope fence below (they travel over NVLink concurrently).
+    __syncwarp();
+    consumer_barrier();  // record complete in this GPU's buffer (visible CTA-wide)
+    for (int i = ctid; i < B2_LINEARIZED_DOUBLES * (sig.n_peers - 1); i += kCT) {
+      int p = i / B2_LINEARIZED_DOUBLES;
+      const int k = i - p * B2_LINEARIZED_DOUBLES;
+      if (p >= sig.my_rank) p++;
+      sig.peer_out[p][static_cast<size_t>(d.out_index) * B2_LINEARIZED_DOUBLES + k] = rec[k];
+    }
+  }
+  __threadfence_system();  // `out` may be mapped host memory (zero-copy host API) / peer memory
+  consumer_barrier();
+  if (ctid == 0) signal_done(sig);  // every writer of this record fenced before the barrier
+  (void)kCT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
+// SINGLE: the launch covers exactly one factor and its pose is the by-value parameter `pose` (linearize: the
+// linearization point; error: the evaluation point); otherwise poses are read from poses_lin / poses_eval.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename PT, typename CT, int KIND, int MODE, bool SINGLE>
+__global__ void __launch_bounds__(kThreads, 1)
+factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
+              const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
+              const __grid_constant__ DoneSignal sig, const __grid_constant__ PoseArg pose) {
+  using L = Layout<PT, CT, MODE>;
+  using XS = XyzStage<PT, MODE>;
+  using CS = CovStage<CT>;
+  __shared__ Shared sh;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kP) {
+    sh.tail[tid] = 0u;
+    sh.head[tid] = 0u;
+    sh.done[tid] = 0u;
+    sh.ack[tid] = 0u;
+    sh.flush[tid] = 0u;
+#pragma unroll
+    for (int s = 0; s < kSC; s++) sh.tile_end[tid][s] = 0u;
+#pragma unroll
+    for (int s = 0; s < kSX; s++) mbar_init(&sh.bar_x[tid][s], 1u);
+#pragma unroll
+    for (int s = 0; s < kSC; s++) mbar_init(&sh.bar_c[tid][s], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t G = gridDim.x;
+  const uint32_t tile_lo = cta_tile_begin(blockIdx.x, num_tiles, G);
+  const uint32_t tile_hi = cta_tile_begin(blockIdx.x + 1, num_tiles, G);
+
+  if (warp < kP) {
+    // ================================================= PROBE warps =================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_PRODUCER));
+    const int p = warp;
+    unsigned char* const wbase = dyn_smem + static_cast<size_t>(p) * L::kWarpBytes;
+    const uint32_t xyz_s = smem_u32(wbase + L::kXyzOff), cov_s = smem_u32(wbase + L::kCovOff);
+    double2* const ring = reinterpret_cast<double2*>(wbase + L::kRingOff);
+    uint32_t tail = 0u, run = 0u;
+    uint32_t nx = 0u, nc = 0u;  // warp tiles whose coordinate / covariance stage has been consumed so far (all runs): stage = n % S, parity = (n / S) & 1
+    uint32_t head_seen = 0u;
+    uint32_t tile = tile_lo;
+    while (tile < tile_hi) {
+      const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
+      const uint32_t n = dg->n;
+      const uint32_t n_pad = dg->n_pad;
+      const uint32_t f_tile_begin = dg->tile_begin;
+      const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
+      const uint32_t out_index = dg->out_index;
+      const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
+      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
+      const double* __restrict__ records = dg->records;
+      int32_t* __restrict__ corr = dg->corr;
+      const VoxelBucket* __restrict__ buckets = dg->buckets;
+      const uint32_t bucket_mask = dg->bucket_mask;
+      const double inv_leaf = dg->inv_leaf;
+      if (!SINGLE) {
+        __syncwarp();
+        if (lane < 12) {
+          const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(out_index) * 16;
+          sh.probe_pose[p][lane] = __ldg(pe + (lane < 9 ? (lane / 3) * 4 + lane % 3 : (lane - 9) * 4 + 3));
+        }
+        __syncwarp();
+      }
+      // pose the correspondences are searched at: constant-bank operands (SINGLE) or this warp's shared-memory slot
+      auto Rm = [&](int i) -> double { return SINGLE ? pose.m[(i / 3) * 4 + (i % 3)] : sh.probe_pose[p][i]; };
+      auto tv = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : sh.probe_pose[p][9 + i]; };
+      const KdTreeView tview{dg->nodes, dg->leaf_pts, static_cast<int>(dg->leaf_f32)};
+      const double max_sq = dg->max_sq;
+
+      // Virtual tile v of the factor (the CTA owns a contiguous range of them) is physical tile (v * S) mod n_tiles with
+      // S ~ 0.618 n_tiles coprime to n_tiles: every CTA samples the (Morton-ordered) cloud quasi-uniformly.
+      const uint32_t f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
+      auto phys_tile = [&](uint32_t vt) { return static_cast<uint32_t>(static_cast<unsigned long long>(vt - f_tile_begin) * perm_stride % f_num_tiles); };
+      auto next_tile = [&](uint32_t pt) {
+        pt += perm_stride;
+        return pt >= f_num_tiles ? pt - f_num_tiles : pt;
+      };
+      // elements of the warp tile that exist in the padded planes (multiple of 32; 0 beyond the cloud)
+      auto tile_count = [&](uint32_t base) -> uint32_t { return base >= n_pad ? 0u : min(static_cast<uint32_t>(kWarpPoints), n_pad - base); };
+      // ---- bulk-copy issue (lane 0 only) ----
+      auto issue_xyz = [&](uint32_t pt, uint32_t k) {  // k: running stage counter of the tile
+        const uint32_t s = k % kSX;
+        const uint32_t base = pt * kTile + p * kWarpPoints, cnt = tile_count(base);
+        uint64_t* bar = &sh.bar_x[p][s];
+        const uint32_t dst = xyz_s + s * XS::kBytes;
+        mbar_expect_tx(bar, cnt * (3u * static_cast<uint32_t>(sizeof(PT)) + (MODE == MODE_ERROR ? 4u : 0u)));
+        if (cnt) {
+          const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(PT));
+#pragma unroll
+          for (int a = 0; a < 3; a++) bulk_g2s(dst + a * XS::kPlane, px + static_cast<size_t>(a) * n_pad + base, bytes, bar);
+          if (MODE == MODE_ERROR) bulk_g2s(dst + XS::kCorrOff, corr + base, cnt * 4u, bar);
+        }
+      };
+      auto issue_cov = [&](uint32_t pt, uint32_t k) {
+        const uint32_t s = k % kSC;
+        const uint32_t base = pt * kTile + p * kWarpPoints, cnt = tile_count(base);
+        uint64_t* bar = &sh.bar_c[p][s];
+        const uint32_t dst = cov_s + s * CS::kBytes;
+        mbar_expect_tx(bar, cnt * 6u * static_cast<uint32_t>(sizeof(CT)));
+        if (cnt) {
+          const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(CT));
+#pragma unroll
+          for (int a = 0; a < 6; a++) bulk_g2s(dst + a * CS::kPlane, cv + static_cast<size_t>(a) * n_pad + base, bytes, bar);
+        }
+      };
+
+      const uint32_t K = run_end - tile;  // warp tiles of this run
+      uint32_t grid_base = tail;          // the accumulate warp's batches of this run start at grid_base + 32 i (until a forced boundary)
+      // prologue: every stage is free (the previous run was drained and acknowledged)
+      uint32_t pt_x = phys_tile(tile), pt_c = pt_x, pt_cur = pt_x;
+      if (lane == 0) fence_proxy_async();
+      for (uint32_t k = 0; k < static_cast<uint32_t>(kSX - 1) && k < K; k++) {
+        if (lane == 0) issue_xyz(pt_x, nx + k);
+        pt_x = next_tile(pt_x);
+      }
+      for (uint32_t k = 0; k < static_cast<uint32_t>(kLC) && k < K; k++) {
+        if (lane == 0) issue_cov(pt_c, nc + k);
+        pt_c = next_tile(pt_c);
+      }
+
+#pragma unroll 1
+      for (uint32_t k = 0; k < K; k++, pt_cur = next_tile(pt_cur)) {
+        // ---- lookahead issues ----
+        if (k + kSX - 1 < K) {  // the stage of tile k - 1: this warp finished reading it (the ballot below synchronised the lanes)
+          if (lane == 0) {
+            fence_proxy_async();
+            issue_xyz(pt_x, nx + kSX - 1);
+          }
+          pt_x = next_tile(pt_x);
+        }
+        if (k + kLC < K) {
+          // covariance stage of tile k + kLC - kSC: free once the accumulate warp has consumed that tile's last hit
+          const uint32_t s = (nc + kLC) % kSC;
+          const uint32_t e = sh.tile_end[p][s];
+          if (static_cast<int32_t>(head_seen - e) < 0) {
+            head_seen = ld_acquire(&sh.head[p]);
+            if (static_cast<int32_t>(head_seen - e) < 0) {
+              // can the accumulate warp get there with full batches?  (deterministic: depends on hit counts only)
+              const uint32_t need = grid_base + ((e - grid_base + 31u) & ~31u);
+              if (static_cast<int32_t>(tail - need) < 0) {
+                if (lane == 0) st_release(&sh.flush[p], tail);  // forced batch boundary at the current tail
+                grid_base = tail;
+              }
+              Backoff bo(32u, 256u);
+              do {
+                bo.wait();
+                head_seen = ld_acquire(&sh.head[p]);
+              } while (static_cast<int32_t>(head_seen - e) < 0);
+            }
+          }
+          if (lane == 0) {
+            fence_proxy_async();
+            issue_cov(pt_c, nc + kLC);
+          }
+          pt_c = next_tile(pt_c);
+        }
+
+        // ---- this tile's coordinates ----
+        const uint32_t sx = nx % kSX;
+        mbar_wait(&sh.bar_x[p][sx], (nx / kSX) & 1u);
+        const unsigned char* xs = wbase + L::kXyzOff + sx * XS::kBytes;
+        const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
+        double u[kPPL][3];
+        int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
+        uint32_t grp_idx[kPPL];
+        bool ok[kPPL];
+        BucketGroup grp[kPPL];
+#pragma unroll
+        for (int q = 0; q < kPPL; q++) {
+          const int li = lane + 32 * q;
+          ok[q] = base + 32 * q < n;
+          const double x = static_cast<double>(reinterpret_cast<const PT*>(xs)[li]);
+          const double y = static_cast<double>(reinterpret_cast<const PT*>(xs + XS::kPlane)[li]);
+          const double z = static_cast<double>(reinterpret_cast<const PT*>(xs + 2 * XS::kPlane)[li]);
+          id[q] = -1;
+          if (MODE == MODE_ERROR) id[q] = ok[q] ? reinterpret_cast<const int*>(xs + XS::kCorrOff)[li] : -1;
+          // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
+          u[q][0] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
+          u[q][1] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
+          u[q][2] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
+          if (MODE == MODE_LINEARIZE && KIND == 0) {
+            cx[q] = voxel_coord1(__dadd_rn(u[q][0], tv(0)), inv_leaf);
+            cy[q] = voxel_coord1(__dadd_rn(u[q][1], tv(1)), inv_leaf);
+            cz[q] = voxel_coord1(__dadd_rn(u[q][2], tv(2)), inv_leaf);
+            grp_idx[q] = voxel_hash(cx[q], cy[q], cz[q]) & bucket_mask;
+#ifndef B2_V2_DEBUG_NO_PROBE
+            grp[q] = load_group(buckets, grp_idx[q]);
+#endif
+          }
+        }
+        uint32_t mask[kPPL], cnt = 0u;
+#pragma unroll
+        for (int q = 0; q < kPPL; q++) {
+          if (MODE == MODE_LINEARIZE) {
+            if (KIND == 0) {
+#ifdef B2_V2_DEBUG_NO_PROBE
+              id[q] = static_cast<int>(grp_idx[q] & 0xffffu);  // measurement aid: no table access, every point "hits" some record
+#else
+              id[q] = match_group(grp[q], cx[q], cy[q], cz[q]);
+#endif
+              uint32_t g = grp_idx[q];
+              while (id[q] == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
+                g = (g + 1) & bucket_mask;
+                id[q] = match_group(load_group(buckets, g), cx[q], cy[q], cz[q]);
+              }
+            } else {
+              double sq;
+              id[q] = kdtree_nn1_warp(tview, __dadd_rn(u[q][0], tv(0)), __dadd_rn(u[q][1], tv(1)), __dadd_rn(u[q][2], tv(2)), ok[q], max_sq, &sq);
+            }
+            if (ok[q]) corr[base + 32 * q] = id[q];
+          }
+          mask[q] = __ballot_sync(0xffffffffu, ok[q] && id[q] >= 0);  // also: every lane is done with the coordinate stage
+          cnt += __popc(mask[q]);
+        }
+        nx++;
+        const uint32_t sc = nc % kSC;
+        if (cnt != 0u) {
+          // room in the ring
+          if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
+            head_seen = ld_acquire(&sh.head[p]);
+            if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
+              Backoff bo(32u, 256u);
+              do {
+                bo.wait();
+                head_seen = ld_acquire(&sh.head[p]);
+              } while (tail + cnt - head_seen > static_cast<uint32_t>(kRing));
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kPPL; q++) {
+            if ((mask[q] >> lane) & 1u) {
+              const uint32_t slot = (tail + __popc(mask[q] & ((1u << lane) - 1u))) & (kRing - 1);
+              const uint32_t loc = sc * kWarpPoints + lane + 32 * q;  // where the accumulate warp finds this point's covariance
+              const unsigned long long bits = static_cast<unsigned long long>(loc) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
+              ring[slot] = make_double2(u[q][0], u[q][1]);
+              ring[kRing + slot] = make_double2(u[q][2], __longlong_as_double(static_cast<long long>(bits)));
+#if B2_V2_PREFETCH_RECORDS
+              const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(id[q]) * kRecordDoubles);
+              prefetch_l2(rec);
+              prefetch_l2(rec + 72);
+#endif
+            }
+            tail += __popc(mask[q]);
+          }
+        }
+        // the tile's covariances must have landed before its hits become visible to the accumulate warp
+        mbar_wait(&sh.bar_c[p][sc], (nc / kSC) & 1u);
+        nc++;
+        __syncwarp();
+        if (lane == 0) {
+          sh.tile_end[p][sc] = tail;
+          st_release(&sh.tail[p], tail);
+        }
+      }
+      // end of this CTA's run of the factor: publish, then wait until the accumulate warp has drained the ring
+      run++;
+      __syncwarp();
+      if (lane == 0) st_release(&sh.done[p], run);
+      {
+        Backoff bo(128u, 512u);
+        while (ld_acquire(&sh.ack[p]) != run) bo.wait();
+      }
+      head_seen = tail;
+      tile = run_end;
+    }
+  } else {
+    // =============================================== ACCUMULATE warps ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_CONSUMER));
+    const int cw = warp - kP;        // accumulate warp index
+    const int ctid = tid - kP * 32;  // thread index within the accumulate group
+    unsigned char* const recbuf = dyn_smem + L::kRecOff + static_cast<size_t>(cw) * 2u * kRecBufBytes;
+    uint32_t head[kRingsPerConsumer];  // items taken (fetched) from each of this warp's rings
+#pragma unroll
+    for (int r = 0; r < kRingsPerConsumer; r++) head[r] = 0u;
+    uint32_t run = 0u;
+    uint32_t tile = tile_lo;
+    double acc[kAcc];
+    while (tile < tile_hi) {
+      const uint32_t f = SINGLE ? 0u : __ldg(tile_factor + tile);
+      consumer_barrier();  // previous flush is done with sh.desc
+      if (ctid < static_cast<int>(sizeof(FactorDesc) / 4)) reinterpret_cast<uint32_t*>(&sh.desc)[ctid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + ctid);
+      consumer_barrier();
+      const FactorDesc& d = sh.desc;
+      const double* pe = SINGLE ? pose.m : ((MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16);
+      if (ctid < 21) {
+        const double* pl = (MODE == MODE_ERROR) ? d.lin_pose : pe;
+        if (ctid < 9)
+          sh.R[ctid] = pe[(ctid / 3) * 4 + ctid % 3];
+        else if (ctid < 12)
+          sh.t[ctid - 9] = pe[(ctid - 9) * 4 + 3];
+        else
+          sh.RL[ctid - 12] = pl[((ctid - 12) / 3) * 4 + (ctid - 12) % 3];
+      }
+      consumer_barrier();
+      // pose operands of the arithmetic: constant bank where the launch allows it, else registers
+      constexpr bool kConstRL = SINGLE && MODE == MODE_LINEARIZE;
+      double RLr[kConstRL ? 1 : 9], tr[SINGLE ? 1 : 3];
+      if (!kConstRL) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) RLr[k] = sh.RL[k];
+      }
+      if (!SINGLE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) tr[k] = sh.t[k];
+      }
+      auto rl = [&](int i) -> double { return kConstRL ? pose.m[(i / 3) * 4 + (i % 3)] : RLr[kConstRL ? 0 : i]; };
+      auto tt = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : tr[SINGLE ? 0 : i]; };
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
+      const double* __restrict__ records = d.records;
+      const uint32_t run_end = min(tile_hi, d.tile_begin + d.num_tiles);
+      run++;
+
+      // One batch = up to 32 consecutive hits of one ring.  `cur` is being computed, `nxt` has been fetched (its target
+      // records are on their way into the other half of the record buffer).
+      struct Bat {
+        uint32_t hd, nb;
+        int r;
+        bool fin, valid;
+      };
+      constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
+      uint32_t finished = 0u;  // rings whose final batch of this run has been FETCHED
+      int rot = 0;             // next ring in the strict rotation
+      uint32_t buf = 0u;
+
+      // take the next batch of ring r if it is there (blocking: wait for it); on success the records are requested
+      auto fetch = [&](int r, bool blocking, Bat& b, uint32_t which) -> bool {
+        const int p = cw + r * kC;
+        uint32_t hd = 0u;
+#pragma unroll
+        for (int k = 0; k < kRingsPerConsumer; k++)
+          if (k == r) hd = head[k];
+        uint32_t nb = 0u;
+        bool fin = false;
+        Backoff bo(32u, 128u);
+        while (true) {
+          const uint32_t dn = ld_acquire(&sh.done[p]);
+          const uint32_t fl = ld_acquire(&sh.flush[p]);
+          const uint32_t tl = ld_acquire(&sh.tail[p]);
+          const uint32_t avail = tl - hd;
+          if (avail >= kBatch) {
+            nb = kBatch;
+            break;
+          }
+          if (static_cast<int32_t>(fl - hd) > 0) {  // forced boundary: the probe warp waits for this short batch
+            nb = fl - hd;
+            break;
+          }
+          if (dn == run) {  // the probe warp finished this run: `tl` is final
+            nb = avail;
+            fin = true;
+            break;
+          }
+          if (!blocking) return false;
+          bo.wait();
+        }
+        b.hd = hd;
+        b.nb = nb;
+        b.r = r;
+        b.fin = fin;
+        b.valid = true;
+#pragma unroll
+        for (int k = 0; k < kRingsPerConsumer; k++)
+          if (k == r) head[k] = hd + nb;
+        if (fin) finished |= 1u << r;
+        // request the target records of the batch: 5 x 16 B per hit, straight into shared memory (no registers, no scoreboard)
+        if (static_cast<uint32_t>(lane) < nb) {
+          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + static_cast<size_t>(p) * L::kWarpBytes + L::kRingOff);
+          const uint32_t slot = (hd + lane) & (kRing - 1);
+          const int id = static_cast<int>(static_cast<unsigned long long>(__double_as_longlong(rg[kRing + slot].y)) >> 32);
+          const char* src = reinterpret_cast<const char*>(records + static_cast<size_t>(id) * kRecordDoubles);
+          const uint32_t dst = smem_u32(recbuf + which * kRecBufBytes + lane * (kRecordDoubles * 8));
+#pragma unroll
+          for (int k = 0; k < 5; k++) cp_async16(dst + 16 * k, src + 16 * k);
+        }
+        cp_async_commit();
+        return true;
+      };
+      auto next_ring = [&](int from) -> int {  // first unfinished ring at or after `from` in the rotation (-1: none)
+#pragma unroll
+        for (int k = 0; k < kRingsPerConsumer; k++) {
+          const int r = (from + k) % kRingsPerConsumer;
+          if (!(finished & (1u << r))) return r;
+        }
+        return -1;
+      };
+
+      Bat cur{0u, 0u, 0, false, false}, nxt{0u, 0u, 0, false, false};
+      while (true) {
+        if (!cur.valid) {
+          const int r = next_ring(rot);
+          if (r < 0) break;
+          fetch(r, true, cur, buf);
+          rot = (r + 1) % kRingsPerConsumer;
+        }
+        // try to get the following batch on its way before computing this one
+        nxt.valid = false;
+        {
+          const int r = next_ring(rot);
+          if (r >= 0 && fetch(r, false, nxt, buf ^ 1u)) rot = (r + 1) % kRingsPerConsumer;
+        }
+        if (nxt.valid)
+          cp_async_wait<1>();
+        else
+          cp_async_wait<0>();
+        // ---- compute `cur` from shared memory only ----
+        {
+          const int p = cw + cur.r * kC;
+          const unsigned char* wb = dyn_smem + static_cast<size_t>(p) * L::kWarpBytes;
+          const double2* rg = reinterpret_cast<const double2*>(wb + L::kRingOff);
+          const bool valid = static_cast<uint32_t>(lane) < cur.nb;
+          const uint32_t slot = (cur.hd + lane) & (kRing - 1);
+          const double2 q0 = rg[slot], q1 = rg[kRing + slot];
+          const uint32_t loc = valid ? static_cast<uint32_t>(static_cast<unsigned long long>(__double_as_longlong(q1.y))) : 0u;
+#ifndef B2_V2_DEBUG_NO_ACCUM
+          if (valid) {  // uniform for full batches
+            const double2* rr = reinterpret_cast<const double2*>(recbuf + buf * kRecBufBytes + lane * (kRecordDoubles * 8));
+            TargetRec T;
+            T.r01 = rr[0];
+            T.r23 = rr[1];
+            T.r45 = rr[2];
+            T.r67 = rr[3];
+            T.r89 = rr[4];
+            const uint32_t cs = loc / kWarpPoints, li = loc % kWarpPoints;
+            const CT* cp = reinterpret_cast<const CT*>(wb + L::kCovOff + cs * CS::kBytes) + li;
+            SourceCov A;
+            A.a00 = static_cast<double>(cp[0]);
+            A.a01 = static_cast<double>(cp[kWarpPoints]);
+            A.a02 = static_cast<double>(cp[2 * kWarpPoints]);
+            A.a11 = static_cast<double>(cp[3 * kWarpPoints]);
+            A.a12 = static_cast<double>(cp[4 * kWarpPoints]);
+            A.a22 = static_cast<double>(cp[5 * kWarpPoints]);
+            accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
+          }
+#else
+          if (valid) acc[28] += q0.x * 0.0 + 1.0 + static_cast<double>(loc) * 0.0;  // measurement aid: probe-side throughput only
+#endif
+          // operands read: hand the ring slots (and the covariance stages behind them) back to the probe warp
+          __syncwarp();
+          if (lane == 0) {
+            st_release(&sh.head[p], cur.hd + cur.nb);
+            if (cur.fin) st_release(&sh.ack[p], run);
+          }
+        }
+        cur = nxt;
+        buf ^= 1u;
+      }
+      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, pe, sig);
+      tile = run_end;
+    }
+  }
+}
+
+}  // namespace B2_V2_NAMESPACE
+}  // namespace b2

@@ -104,42 +104,10 @@ __host__ __device__ __forceinline__ uint32_t cta_tile_begin(uint32_t c, uint32_t
   return static_cast<uint32_t>(static_cast<unsigned long long>(c) * T / G);
 }
 
-// stride S ~ n / golden ratio with gcd(S, n) == 1: v -> (v * S) mod n is a permutation that spreads any run of v evenly
-inline uint32_t golden_stride(uint32_t n) {
-  if (n <= 2u) return 1u;
-  uint32_t s = static_cast<uint32_t>(static_cast<double>(n) * 0.6180339887498949);
-  if (s < 1u) s = 1u;
-  auto gcd = [](uint32_t a, uint32_t b) {
-    while (b) {
-      const uint32_t r = a % b;
-      a = b;
-      b = r;
-    }
-    return a;
-  };
-  while (gcd(s, n) != 1u) s++;
-  return s % n == 0u ? 1u : s % n;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Per-factor flush by the accumulate warpgroup(s): warp butterfly -> cross-warp sum -> fixed slot; the last CTA of the
 // factor sums the slots in slot order and runs the epilogue (H_t = X^T A' X, ...).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void signal_done(const DoneSignal& sig) {
-  // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
-  if (sig.flag == nullptr) return;
-  const unsigned int prev = atomicAdd(sig.counter, 1u);
-  if (prev == sig.total - 1u) {  // every factor of this call is done: re-arm the counter, publish the sequence number
-    *sig.counter = 0u;
-    __threadfence_system();
-    if (sig.n_peers > 0) {
-      for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
-    } else {
-      *sig.flag = sig.seq;
-    }
-  }
-}
-
 template <int MODE>
 __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int ctid, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
                                              const double* __restrict__ poses_lin, const DoneSignal& sig) {
@@ -253,7 +221,7 @@ template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
               const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-              const DoneSignal sig) {
+              const DoneSignal sig, const PoseArg /*pose: by-value poses are a feature of the v2 kernel*/) {
   __shared__ Shared sh;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double2* const rings = reinterpret_cast<double2*>(dyn_smem);
@@ -511,9 +479,10 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 #pragma unroll
         for (int k = 0; k < kRingsPerConsumer; k++)
           if (k == r) hd = head[k];
-        // Hand back the slots of every batch taken so far: the previous batch of this ring went through its arithmetic
-        // before the rotation came back here (its shared-memory reads completed long ago), so this loop needs no fence.
-        if (lane == 0) st_volatile(&sh.head[p], hd);
+        // Hand back the slots of every batch taken so far.  All lanes must have finished reading them: converge the warp,
+        // then release (independent thread scheduling gives no such guarantee by itself).
+        __syncwarp();
+        if (lane == 0) st_release(&sh.head[p], hd);
         uint32_t nb = 0u;
         bool fin = false;
         {

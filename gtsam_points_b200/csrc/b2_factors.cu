@@ -58,6 +58,44 @@ struct DoneSignal {
   unsigned int* peer_flag[kMaxPeers];   // each GPU's flag array [n_peers]
 };
 
+// stride S ~ n / golden ratio with gcd(S, n) == 1: v -> (v * S) mod n is a permutation that spreads any run of v evenly
+inline uint32_t golden_stride(uint32_t n) {
+  if (n <= 2u) return 1u;
+  uint32_t s = static_cast<uint32_t>(static_cast<double>(n) * 0.6180339887498949);
+  if (s < 1u) s = 1u;
+  auto gcd = [](uint32_t a, uint32_t b) {
+    while (b) {
+      const uint32_t r = a % b;
+      a = b;
+      b = r;
+    }
+    return a;
+  };
+  while (gcd(s, n) != 1u) s++;
+  return s % n == 0u ? 1u : s % n;
+}
+
+// Pose of a single-factor launch, passed BY VALUE as a kernel parameter (row-major 4x4): the arithmetic takes it as
+// constant-bank operands and the kernel reads nothing from host memory on its way in.
+struct PoseArg {
+  double m[16];
+};
+
+// called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
+__device__ __forceinline__ void signal_done(const DoneSignal& sig) {
+  if (sig.flag == nullptr) return;
+  const unsigned int prev = atomicAdd(sig.counter, 1u);
+  if (prev == sig.total - 1u) {  // every factor of this call is done: re-arm the counter, publish the sequence number
+    *sig.counter = 0u;
+    __threadfence_system();
+    if (sig.n_peers > 0) {
+      for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
+    } else {
+      *sig.flag = sig.seq;
+    }
+  }
+}
+
 struct FactorDesc {
   const void* pts;    // 3 planes of n_pad
   const void* covs;   // 6 planes of n_pad
@@ -240,27 +278,29 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return fma(r, e, r);
 }
 
-template <int MODE>
-__device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const double (&RL)[9], const double (&t)[3], double v0, double v1, double v2,
-                                                 const TargetRec& T, const SourceCov& A) {
+// RLf(i) / tf(i): accessors of the linearization rotation (row-major) and the translation of the evaluation pose -- arrays in
+// registers, or by-value kernel parameters (constant-bank operands) for single-factor launches.
+template <int MODE, class RLF, class TF>
+__device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RLF& RLf, const TF& tf, double v0, double v1, double v2, const TargetRec& T,
+                                                   const SourceCov& A) {
   const double mb0 = T.r01.x, mb1 = T.r01.y, mb2 = T.r23.x;
   const double b00 = T.r23.y, b01 = T.r45.x, b02 = T.r45.y, b11 = T.r67.x, b12 = T.r67.y, b22 = T.r89.x;
   // fused covariance S = C_B + RL C_A RL^T (symmetric), M = S^-1 (cofactors / det)
-  const double t00 = RL[0] * A.a00 + RL[1] * A.a01 + RL[2] * A.a02;
-  const double t01 = RL[0] * A.a01 + RL[1] * A.a11 + RL[2] * A.a12;
-  const double t02 = RL[0] * A.a02 + RL[1] * A.a12 + RL[2] * A.a22;
-  const double s00 = b00 + (t00 * RL[0] + t01 * RL[1] + t02 * RL[2]);
-  const double s01 = b01 + (t00 * RL[3] + t01 * RL[4] + t02 * RL[5]);
-  const double s02 = b02 + (t00 * RL[6] + t01 * RL[7] + t02 * RL[8]);
-  const double t10 = RL[3] * A.a00 + RL[4] * A.a01 + RL[5] * A.a02;
-  const double t11 = RL[3] * A.a01 + RL[4] * A.a11 + RL[5] * A.a12;
-  const double t12 = RL[3] * A.a02 + RL[4] * A.a12 + RL[5] * A.a22;
-  const double s11 = b11 + (t10 * RL[3] + t11 * RL[4] + t12 * RL[5]);
-  const double s12 = b12 + (t10 * RL[6] + t11 * RL[7] + t12 * RL[8]);
-  const double t20 = RL[6] * A.a00 + RL[7] * A.a01 + RL[8] * A.a02;
-  const double t21 = RL[6] * A.a01 + RL[7] * A.a11 + RL[8] * A.a12;
-  const double t22 = RL[6] * A.a02 + RL[7] * A.a12 + RL[8] * A.a22;
-  const double s22 = b22 + (t20 * RL[6] + t21 * RL[7] + t22 * RL[8]);
+  const double t00 = RLf(0) * A.a00 + RLf(1) * A.a01 + RLf(2) * A.a02;
+  const double t01 = RLf(0) * A.a01 + RLf(1) * A.a11 + RLf(2) * A.a12;
+  const double t02 = RLf(0) * A.a02 + RLf(1) * A.a12 + RLf(2) * A.a22;
+  const double s00 = b00 + (t00 * RLf(0) + t01 * RLf(1) + t02 * RLf(2));
+  const double s01 = b01 + (t00 * RLf(3) + t01 * RLf(4) + t02 * RLf(5));
+  const double s02 = b02 + (t00 * RLf(6) + t01 * RLf(7) + t02 * RLf(8));
+  const double t10 = RLf(3) * A.a00 + RLf(4) * A.a01 + RLf(5) * A.a02;
+  const double t11 = RLf(3) * A.a01 + RLf(4) * A.a11 + RLf(5) * A.a12;
+  const double t12 = RLf(3) * A.a02 + RLf(4) * A.a12 + RLf(5) * A.a22;
+  const double s11 = b11 + (t10 * RLf(3) + t11 * RLf(4) + t12 * RLf(5));
+  const double s12 = b12 + (t10 * RLf(6) + t11 * RLf(7) + t12 * RLf(8));
+  const double t20 = RLf(6) * A.a00 + RLf(7) * A.a01 + RLf(8) * A.a02;
+  const double t21 = RLf(6) * A.a01 + RLf(7) * A.a11 + RLf(8) * A.a12;
+  const double t22 = RLf(6) * A.a02 + RLf(7) * A.a12 + RLf(8) * A.a22;
+  const double s22 = b22 + (t20 * RLf(6) + t21 * RLf(7) + t22 * RLf(8));
 
   const double c00 = s11 * s22 - s12 * s12;
   const double c01 = s02 * s12 - s01 * s22;
@@ -273,7 +313,7 @@ __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const doub
   const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
 
   // residual r = mean_B - (u + t), Mahalanobis error
-  const double e0 = mb0 - __dadd_rn(v0, t[0]), e1 = mb1 - __dadd_rn(v1, t[1]), e2 = mb2 - __dadd_rn(v2, t[2]);
+  const double e0 = mb0 - __dadd_rn(v0, tf(0)), e1 = mb1 - __dadd_rn(v1, tf(1)), e2 = mb2 - __dadd_rn(v2, tf(2));
   const double w0 = m00 * e0 + m01 * e1 + m02 * e2;
   const double w1 = m01 * e0 + m11 * e1 + m12 * e2;
   const double w2 = m02 * e0 + m12 * e1 + m22 * e2;
@@ -317,6 +357,12 @@ __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const doub
   }
 }
 
+template <int MODE>
+__device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const double (&RL)[9], const double (&t)[3], double v0, double v1, double v2,
+                                                 const TargetRec& T, const SourceCov& A) {
+  accumulate_point_f<MODE>(acc, [&](int i) { return RL[i]; }, [&](int i) { return t[i]; }, v0, v1, v2, T, A);
+}
+
 // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
 __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, double y, double z, double& u0, double& u1, double& u2) {
   u0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0], x), __dmul_rn(R[1], y)), __dmul_rn(R[2], z));
@@ -327,48 +373,50 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 }  // namespace b2
 
 // ---- kernel configurations -------------------------------------------------------------------------------------
-// VGICP (voxel hash probe): probe and accumulate work are comparable -> 8 probe + 8 accumulate warps.
-#define B2_WS_NAMESPACE ws
-#ifndef B2_WS_PRODUCERS
-#define B2_WS_PRODUCERS 8
+// VGICP (voxel hash probe): the v2 kernel (TMA-staged streams, shared-memory-fed accumulate warps).
+#define B2_V2_NAMESPACE v2
+#ifndef B2_V2_PRODUCERS
+#define B2_V2_PRODUCERS 8
 #endif
-#ifndef B2_WS_CONSUMERS
-#define B2_WS_CONSUMERS 8
+#ifndef B2_V2_CONSUMERS
+#define B2_V2_CONSUMERS 8
 #endif
-#ifndef B2_WS_REGS_PRODUCER
-#define B2_WS_REGS_PRODUCER 88
+#ifndef B2_V2_REGS_PRODUCER
+#define B2_V2_REGS_PRODUCER 88
 #endif
-#ifndef B2_WS_REGS_CONSUMER
-#define B2_WS_REGS_CONSUMER 168
+#ifndef B2_V2_REGS_CONSUMER
+#define B2_V2_REGS_CONSUMER 168
 #endif
-#ifndef B2_WS_RING
-#define B2_WS_RING 256
+#ifndef B2_V2_RING
+#define B2_V2_RING 128
 #endif
-#ifndef B2_WS_PPL
-#define B2_WS_PPL 2
+#ifndef B2_V2_PPL
+#define B2_V2_PPL 2
 #endif
-#ifndef B2_WS_IPL
-#define B2_WS_IPL 1  // correspondences per accumulate lane and batch
+#ifndef B2_V2_XYZ_STAGES
+#define B2_V2_XYZ_STAGES 3
 #endif
-#ifndef B2_WS_COORDS_AHEAD
-#define B2_WS_COORDS_AHEAD 0  // 1: probe warps load the coordinates of tile k+1 into registers before working on tile k
+#ifndef B2_V2_COV_STAGES
+#define B2_V2_COV_STAGES 4
 #endif
-#ifndef B2_WS_PREFETCH_OPERANDS
-#define B2_WS_PREFETCH_OPERANDS 1  // probe warps start the voxel record + covariance lines of every hit towards L2
+#ifndef B2_V2_COV_AHEAD
+#define B2_V2_COV_AHEAD 1
 #endif
-#include "b2_factor_kernel_ws.cuh"
-#undef B2_WS_NAMESPACE
-#undef B2_WS_PRODUCERS
-#undef B2_WS_CONSUMERS
-#undef B2_WS_REGS_PRODUCER
-#undef B2_WS_REGS_CONSUMER
-#undef B2_WS_RING
-#undef B2_WS_PPL
-#undef B2_WS_IPL
+#ifndef B2_V2_PREFETCH_RECORDS
+#define B2_V2_PREFETCH_RECORDS 1  // probe warps start the voxel record lines of every hit towards L2
+#endif
+#include "b2_factor_kernel_v2.cuh"
+#undef B2_V2_NAMESPACE
 
 // GICP (kd-tree 1-NN): the tree walk is ~100 dependent loads per point, the accumulate work is unchanged -> many thin
 // probe warps (the walk keeps its stack in local memory and needs few registers) feeding 4 fat accumulate warps.
 #define B2_WS_NAMESPACE ws_gicp
+#ifndef B2_WS_COORDS_AHEAD
+#define B2_WS_COORDS_AHEAD 0
+#endif
+#ifndef B2_WS_PREFETCH_OPERANDS
+#define B2_WS_PREFETCH_OPERANDS 1
+#endif
 #ifndef B2_WS_GICP_PRODUCERS
 #define B2_WS_GICP_PRODUCERS 28
 #endif
@@ -402,14 +450,21 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
 // ---------------------------------------------------------------------------------------------------------------
-using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal);
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal, PoseArg);
 
-template <int MODE>
+template <int MODE, bool SINGLE>
 KernelFn pick_vgicp(int pb, int cb) {
-  if (pb == 4 && cb == 4) return ws::factor_kernel<float, float, 0, MODE>;
-  if (pb == 4 && cb == 8) return ws::factor_kernel<float, double, 0, MODE>;
-  if (pb == 8 && cb == 4) return ws::factor_kernel<double, float, 0, MODE>;
-  return ws::factor_kernel<double, double, 0, MODE>;
+  if (pb == 4 && cb == 4) return v2::factor_kernel<float, float, 0, MODE, SINGLE>;
+  if (pb == 4 && cb == 8) return v2::factor_kernel<float, double, 0, MODE, SINGLE>;
+  if (pb == 8 && cb == 4) return v2::factor_kernel<double, float, 0, MODE, SINGLE>;
+  return v2::factor_kernel<double, double, 0, MODE, SINGLE>;
+}
+template <int MODE>
+size_t vgicp_smem(int pb, int cb) {
+  if (pb == 4 && cb == 4) return v2::Layout<float, float, MODE>::kTotal;
+  if (pb == 4 && cb == 8) return v2::Layout<float, double, MODE>::kTotal;
+  if (pb == 8 && cb == 4) return v2::Layout<double, float, MODE>::kTotal;
+  return v2::Layout<double, double, MODE>::kTotal;
 }
 template <int MODE>
 KernelFn pick_gicp(int pb, int cb) {
@@ -422,15 +477,22 @@ KernelFn pick_gicp(int pb, int cb) {
 // launch shape of a kernel configuration
 struct KernelShape {
   int threads, tile;
-  size_t dyn_smem;
 };
 KernelShape kernel_shape(int kind) {
-  if (kind == 0) return {ws::kThreads, ws::kTile, ws::kRingBytes};
-  return {ws_gicp::kThreads, ws_gicp::kTile, ws_gicp::kRingBytes};
+  if (kind == 0) return {v2::kThreads, v2::kTile};
+  return {ws_gicp::kThreads, ws_gicp::kTile};
+}
+size_t kernel_smem(int kind, int mode, int pb, int cb) {
+  if (kind == 0) return mode == MODE_LINEARIZE ? vgicp_smem<MODE_LINEARIZE>(pb, cb) : vgicp_smem<MODE_ERROR>(pb, cb);
+  return ws_gicp::kRingBytes;
 }
 
-KernelFn pick_kernel(int kind, int mode, int pb, int cb) {
-  if (kind == 0) return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE>(pb, cb) : pick_vgicp<MODE_ERROR>(pb, cb);
+// single == true: the by-value-pose instantiation for launches that cover exactly one factor (VGICP kernel only)
+KernelFn pick_kernel(int kind, int mode, int pb, int cb, bool single) {
+  if (kind == 0) {
+    if (single) return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, true>(pb, cb) : pick_vgicp<MODE_ERROR, true>(pb, cb);
+    return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, false>(pb, cb) : pick_vgicp<MODE_ERROR, false>(pb, cb);
+  }
   return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE>(pb, cb) : pick_gicp<MODE_ERROR>(pb, cb);
 }
 
@@ -440,12 +502,14 @@ constexpr size_t kZeroCopyMaxFactors = 64;
 struct Group {
   int kind, pb, cb;
   std::vector<size_t> members;  // indices into the set's factor list
+  std::vector<uint64_t> gen;    // per member: the factor's params_gen its device descriptor was built from
   FactorDesc* d_descs = nullptr;
   uint32_t* d_tile_factor = nullptr;
   uint32_t num_tiles = 0;
   uint32_t grid[2] = {0, 0};
   KernelFn fn[2] = {nullptr, nullptr};
-  size_t dyn_smem = 0;
+  KernelFn fn_single[2] = {nullptr, nullptr};  // by-value-pose instantiation (only for sets of exactly one factor)
+  size_t dyn_smem[2] = {0, 0};
 };
 
 }  // namespace b2
@@ -515,10 +579,24 @@ b2_status wait_done(b2_ctx* ctx, unsigned int seq) {
   return B2_OK;
 }
 
-b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{}) {
+// h_pose != nullptr: the set holds ONE factor and its pose (16 doubles, host memory) travels by value with the launch
+b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{}, const double* h_pose = nullptr) {
   cudaStream_t st = s->ctx->stream;
+  PoseArg pa{};
+  const bool single = h_pose != nullptr && s->factors.size() == 1 && s->groups.size() == 1 && s->groups[0].fn_single[mode] != nullptr;
+  if (single) std::memcpy(pa.m, h_pose, sizeof(pa.m));
   for (auto& g : s->groups) {
-    g.fn[mode]<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem, st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials, s->d_counters, d_out, sig);
+    // tuning setters called after the set was built (set_max_correspondence_distance): refresh the device descriptors,
+    // stream-ordered before the launch -- like the reference, the new value takes effect at the next correspondence update
+    for (size_t k = 0; k < g.members.size(); k++) {
+      const b2_factor* f = s->factors[g.members[k]];
+      if (f->params_gen != g.gen[k]) {
+        B2_CUDA(cudaMemcpyAsync(&g.d_descs[k].max_sq, &f->max_corr_sq, sizeof(double), cudaMemcpyHostToDevice, st));
+        g.gen[k] = f->params_gen;
+      }
+    }
+    (single ? g.fn_single[mode] : g.fn[mode])<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem[mode], st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials,
+                                                                                                                  s->d_counters, d_out, sig, pa);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -627,10 +705,7 @@ b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist) {
   B2_REQUIRE(f != nullptr, "b2_factor_set_max_correspondence_distance: factor is NULL");
   B2_REQUIRE(dist >= 0.0, "b2_factor_set_max_correspondence_distance: negative distance");
   f->max_corr_sq = dist * dist;  // integrated_gicp_factor.hpp:98-101
-  if (f->self_set) {             // descriptors embed max_sq: rebuild lazily
-    b2_factor_set_destroy(f->self_set);
-    f->self_set = nullptr;
-  }
+  f->params_gen++;               // every factor set holding this factor refreshes its device descriptor before its next launch
   return B2_OK;
 }
 
@@ -726,28 +801,35 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       d.lin_pose = f->d_lin_pose;
       d.tile_begin = tile_cursor;
       d.num_tiles = std::max<uint32_t>(1u, (d.n + shape.tile - 1) / shape.tile);
-      d.perm_stride = ws::golden_stride(d.num_tiles);
+      d.perm_stride = golden_stride(d.num_tiles);
       d.out_index = static_cast<uint32_t>(g.members[k]);
+      g.gen.push_back(f->params_gen);
       tile_cursor += d.num_tiles;
       tile_factor.insert(tile_factor.end(), d.num_tiles, static_cast<uint32_t>(k));
     }
     g.num_tiles = tile_cursor;
     for (int mode = 0; mode < 2; mode++) {
-      g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb);
-      g.dyn_smem = shape.dyn_smem;
+      g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb, false);
+      g.fn_single[mode] = (g.kind == B2_FACTOR_VGICP && F == 1) ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;
+      g.dyn_smem[mode] = kernel_smem(g.kind, mode, g.pb, g.cb);
       int per_sm = 0;
-      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(g.fn[mode]), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem));
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g.fn[mode], shape.threads, g.dyn_smem);
-      if (e != cudaSuccess || per_sm < 1) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: occupancy query failed (%s)", cudaGetErrorString(e)));
+      cudaError_t e = cudaSuccess;
+      for (KernelFn fn : {g.fn[mode], g.fn_single[mode]}) {
+        if (fn == nullptr || e != cudaSuccess) continue;
+        e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.dyn_smem[mode]));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, shape.threads, g.dyn_smem[mode]);
+        if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+      }
+      if (e != cudaSuccess) return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: the kernel does not fit one CTA per SM (%s)", cudaGetErrorString(e)));
       // persistent: one CTA per SM (the kernel redistributes the SM's whole register file between its warp roles)
       const uint32_t G = std::min<uint32_t>(g.num_tiles, static_cast<uint32_t>(ctx->sm_count));
       g.grid[mode] = G;
       // CTA c owns tiles [c T / G, (c + 1) T / G): a factor's partial-sum slots are the CTAs whose range touches it
       uint32_t c = 0;
       for (auto& d : descs) {
-        while (ws::cta_tile_begin(c + 1, g.num_tiles, G) <= d.tile_begin) c++;
+        while (v2::cta_tile_begin(c + 1, g.num_tiles, G) <= d.tile_begin) c++;
         uint32_t c_last = c;
-        while (ws::cta_tile_begin(c_last + 1, g.num_tiles, G) < d.tile_begin + d.num_tiles) c_last++;
+        while (v2::cta_tile_begin(c_last + 1, g.num_tiles, G) < d.tile_begin + d.num_tiles) c_last++;
         d.cta_first[mode] = c;
         d.num_slots[mode] = c_last - c + 1;
         d.slot_begin[mode] = slot_cursor;
@@ -822,6 +904,64 @@ b2_status b2_factor_set_error_device(b2_factor_set* s, const double* d_deltas_ev
     if (!f->linearized) return fail(B2_ERR_INVALID_STATE, "b2_factor_set_error_device: a factor of the set has not been linearized yet");
   B2_CUDA(cudaSetDevice(s->ctx->device));
   B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_deltas_eval, d_out_errors));
+  return B2_OK;
+}
+
+b2_status b2_factor_set_issue_linearize(b2_factor_set* s, const double* deltas, double* d_out) {
+  B2_REQUIRE(s && deltas, "b2_factor_set_issue_linearize: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  const size_t F = s->factors.size();
+  if (d_out == nullptr) d_out = s->d_out;
+  if (F == 1 && s->groups[0].fn_single[MODE_LINEARIZE] != nullptr) {
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, nullptr, nullptr, d_out, DoneSignal{}, deltas));  // pose by value: nothing but the launch
+  } else {
+    // pageable source: the runtime stages it before returning, so the caller's buffer is free immediately
+    B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, deltas, F * 16 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out));
+  }
+  for (size_t i = 0; i < F; i++) {
+    s->factors[i]->linearized = true;
+    std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
+  }
+  return B2_OK;
+}
+
+b2_status b2_factor_set_issue_error(b2_factor_set* s, const double* deltas_eval, double* d_out_errors) {
+  B2_REQUIRE(s && deltas_eval, "b2_factor_set_issue_error: NULL argument");
+  for (auto* f : s->factors)
+    if (!f->linearized) return fail(B2_ERR_INVALID_STATE, "b2_factor_set_issue_error: a factor of the set has not been linearized yet");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  const size_t F = s->factors.size();
+  if (d_out_errors == nullptr) d_out_errors = s->d_err;
+  if (F == 1 && s->groups[0].fn_single[MODE_ERROR] != nullptr) {
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, nullptr, d_out_errors, DoneSignal{}, deltas_eval));
+  } else {
+    B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, deltas_eval, F * 16 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, s->d_poses_eval, d_out_errors));
+  }
+  return B2_OK;
+}
+
+b2_status b2_factor_set_sync(b2_factor_set* s) {
+  B2_REQUIRE(s != nullptr, "b2_factor_set_sync: set is NULL");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  B2_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return B2_OK;
+}
+
+b2_status b2_factor_set_store_linearized(b2_factor_set* s, b2_linearized* out) {
+  B2_REQUIRE(s && out, "b2_factor_set_store_linearized: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  B2_CUDA(cudaMemcpyAsync(out, s->d_out, s->factors.size() * sizeof(b2_linearized), cudaMemcpyDeviceToHost, s->ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return B2_OK;
+}
+
+b2_status b2_factor_set_store_errors(b2_factor_set* s, double* out_errors) {
+  B2_REQUIRE(s && out_errors, "b2_factor_set_store_errors: NULL argument");
+  B2_CUDA(cudaSetDevice(s->ctx->device));
+  B2_CUDA(cudaMemcpyAsync(out_errors, s->d_err, s->factors.size() * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(s->ctx->stream));
   return B2_OK;
 }
 
@@ -925,7 +1065,7 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     t1 = std::chrono::steady_clock::now();
     DoneSignal sig{};
     sig.counter = s->ctx->d_done_counter, sig.flag = s->ctx->d_done_flag, sig.total = static_cast<unsigned int>(F), sig.seq = ++s->ctx->done_seq;
-    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig, F == 1 ? deltas : nullptr));
     t2 = std::chrono::steady_clock::now();
     B2_TRY(wait_done(s->ctx, sig.seq));
   } else {
@@ -973,7 +1113,7 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
     double* d_res = reinterpret_cast<double*>(reinterpret_cast<char*>(d_in) + in_bytes);
     DoneSignal sig{};
     sig.counter = s->ctx->d_done_counter, sig.flag = s->ctx->d_done_flag, sig.total = static_cast<unsigned int>(F), sig.seq = ++s->ctx->done_seq;
-    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res, sig));
+    B2_TRY(launch_groups(s, MODE_ERROR, nullptr, d_in, d_res, sig, F == 1 ? deltas_eval : nullptr));
     B2_TRY(wait_done(s->ctx, sig.seq));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_eval, h, in_bytes, cudaMemcpyHostToDevice, st));

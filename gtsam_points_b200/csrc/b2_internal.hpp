@@ -137,6 +137,7 @@ struct b2_factor {
   const b2_kdtree* tree = nullptr;
   const b2_cloud* source = nullptr;
   double max_corr_sq = 1.0;
+  uint64_t params_gen = 0;  // bumped by every setter that changes a value factor sets have copied into their device descriptors
   int32_t* d_corr = nullptr;       // per stored source position: voxel id / target leaf position, -1 = none
   double* d_target_records = nullptr;  // GICP: target records in leaf order (Nt x 10), owned
   double* d_lin_pose = nullptr;        // 16 doubles: the linearization point, written by the linearize kernel's epilogue

@@ -61,6 +61,10 @@ class ShardedFactorSet:
 
             assert ctx is not None
             self.device = torch.device("cuda", ctx.device)
+            # The library's kernels run on ctx.stream; every torch operation of this class (pose copies, zero_, index_copy_,
+            # all_reduce, D2H) runs on torch's CURRENT stream.  When the two differ they are ordered explicitly around every
+            # library call (_enter_lib / _leave_lib); when they are the same stream the ordering is the stream's.
+            self._lib_stream = torch.cuda.ExternalStream(ctx.stream, device=self.device) if ctx.stream else None
             self.set = NonlinearFactorSetGPU(ctx)
             for f in self.local_factors:
                 self.set.add(f)
@@ -91,6 +95,23 @@ class ShardedFactorSet:
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
                 if int(ok.item()) == 0:
                     self.exchange = None
+
+    # -- stream ordering between torch's current stream and the library's stream -------------------------------------
+    def _enter_lib(self):
+        """Library work enqueued next must see everything torch has enqueued so far on its current stream."""
+        ls = getattr(self, "_lib_stream", None)
+        if ls is not None:
+            cur = self.torch.cuda.current_stream(self.device)
+            if cur.cuda_stream != ls.cuda_stream:
+                ls.wait_stream(cur)
+
+    def _leave_lib(self):
+        """torch work enqueued next (all-reduce, index_copy_, D2H, the next step's pose copy / zero_) waits for the library's kernels."""
+        ls = getattr(self, "_lib_stream", None)
+        if ls is not None:
+            cur = self.torch.cuda.current_stream(self.device)
+            if cur.cuda_stream != ls.cuda_stream:
+                cur.wait_stream(ls)
 
     # -- multi-GPU exchange fused into the kernel's epilogue (peer stores over NVLink instead of an NCCL all-reduce) -----
     def _setup_peer_exchange(self):
@@ -136,11 +157,14 @@ class ShardedFactorSet:
         flag_off = (2 * nrec) * 8 + par * 32                      # this parity's flag words (8 x uint32)
         peer_out = (C.c_void_p * world)(*[p + out_off for p in ex["ptrs"]])
         peer_flag = (C.c_void_p * world)(*[p + flag_off for p in ex["ptrs"]])
+        self._enter_lib()
         if self.local_factors:
             capi.check(capi.lib().b2_factor_set_linearize_exchange(self.set.h, self.d_deltas.data_ptr(), ex["ptrs"][rank] + out_off, peer_out, peer_flag, world, rank, self.step))
         else:  # nothing to linearize on this rank: still take part in the exchange
             capi.check(capi.lib().b2_exchange_signal(self.ctx.h, peer_flag, world, rank, self.step))
         capi.check(capi.lib().b2_exchange_wait(self.ctx.h, ex["ptrs"][rank] + flag_off, world, self.step))
+        self._leave_lib()
+        # NOTE: this view aliases the parity buffer of this step; it is overwritten two steps later (double-buffered by step parity)
         self.d_all = ex["buf"][par * nrec : (par + 1) * nrec].view(self.num_global, RECORD)
         return self.d_all
 
@@ -155,7 +179,9 @@ class ShardedFactorSet:
             direct = self.compute is None and self.contiguous
             dst = self.d_all[self.first : self.first + len(self.local_factors)] if direct else self.d_local
             if self.compute is None:
+                self._enter_lib()  # after the pose copy and zero_() above
                 capi.check(capi.lib().b2_factor_set_linearize_device(self.set.h, self.d_deltas.data_ptr(), dst.data_ptr()))
+                self._leave_lib()  # before index_copy_ / all_reduce / the D2H copy
             else:
                 self.d_local.copy_(torch.as_tensor(np.asarray(self.compute(self.d_deltas.cpu().numpy()))))
             if not direct:

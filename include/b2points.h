@@ -193,6 +193,20 @@ B2_API b2_status b2_factor_set_error(b2_factor_set* set, const double* deltas_ev
  * context's stream.  Asynchronous: no host synchronisation; ordering is the stream's. */
 B2_API b2_status b2_factor_set_linearize_device(b2_factor_set* set, const double* d_deltas, double* d_out);
 B2_API b2_status b2_factor_set_error_device(b2_factor_set* set, const double* d_deltas_eval, double* d_out_errors);
+/* Asynchronous split of the two calls above -- the issue / sync / store protocol of NonlinearFactorGPU
+ * (include/gtsam_points/factors/nonlinear_factor_gpu.hpp:49-121: set_linearization_point + issue_linearize, sync,
+ * store_linearized; set_evaluation_point + issue_compute_error, store_computed_error) at factor-set granularity, which is how
+ * NonlinearFactorSetGPU drives it (src/gtsam_points/cuda/nonlinear_factor_set_gpu.cpp:91-133).
+ *   issue_*: deltas are HOST poses (F x 16), captured before the call returns (a set of one factor passes its pose BY VALUE as
+ *            a kernel parameter: no copy operation at all); the kernels are enqueued on the context's stream and the results
+ *            stay on the device -- in d_out / d_out_errors (device pointers) or, if NULL, in the set's own buffer.
+ *   sync:    waits for everything issued on the set's stream.
+ *   store_*: copies the results of the last issue_* out of the set's own buffer to the host (synchronises itself). */
+B2_API b2_status b2_factor_set_issue_linearize(b2_factor_set* set, const double* deltas, double* d_out);
+B2_API b2_status b2_factor_set_issue_error(b2_factor_set* set, const double* deltas_eval, double* d_out_errors);
+B2_API b2_status b2_factor_set_sync(b2_factor_set* set);
+B2_API b2_status b2_factor_set_store_linearized(b2_factor_set* set, b2_linearized* out);
+B2_API b2_status b2_factor_set_store_errors(b2_factor_set* set, double* out_errors);
 /* Multi-GPU exchange fused into the kernel (one process per GPU, all GPUs of one NVLink / NVSwitch node): like
  * b2_factor_set_linearize_device, and in the same launch the epilogue that finishes a factor also stores its record into
  * the same slot of every peer GPU's result buffer (peer_out[p]: device pointer, valid on THIS device, to peer p's buffer at

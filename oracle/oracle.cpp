@@ -169,7 +169,9 @@ struct XORVec3iHash {
 struct orc_cloud {
   std::vector<Vec4> points;
   std::vector<Mat4> covs;
+  std::vector<Vec4> normals;  // (nx, ny, nz, 0), types/point_cloud.hpp:107
   bool covs_given = false;
+  bool has_normals() const { return normals.size() == points.size() && !points.empty(); }
   size_t size() const { return points.size(); }
   bool has_covs() const { return covs_given; }
 };
@@ -515,8 +517,11 @@ inline void hat3(const double v[3], double h[3][3]) {
 // ---------------------------------------------------------------------------------------------
 struct orc_factor {
   bool is_vgicp;
+  int icp_mode = 0;  // 0: (V)GICP, 1: point-to-point ICP, 2: point-to-plane ICP (integrated_icp_factor_impl.hpp)
   int num_threads = 1;
   double max_correspondence_distance_sq = 1.0;  // integrated_gicp_factor_impl.hpp:30
+  int cache_mode = 0;                           // FusedCovCacheMode: 0 FULL, 1 COMPACT, 2 NONE (integrated_gicp_factor.hpp:20-24)
+  double correspondence_update_tolerance_rot = 0.0, correspondence_update_tolerance_trans = 0.0;  // integrated_gicp_factor_impl.hpp:31-32
 
   const orc_voxelmap* target_voxels = nullptr;
   const orc_cloud* target = nullptr;
@@ -524,22 +529,114 @@ struct orc_factor {
   const orc_cloud* source = nullptr;
 
   Mat4 linearization_point;
+  Mat4 last_correspondence_point;
   std::vector<const GaussianVoxel*> corr_voxels;  // VGICP: integrated_vgicp_factor.hpp:107
   std::vector<long> corr_indices;                 // GICP:  integrated_gicp_factor.hpp:147
   std::vector<Mat4> mahalanobis_full;
+  struct Compact6 {
+    float v[6];
+  };
+  std::vector<Compact6> mahalanobis_compact;  // util/compact.hpp:9-25: (00, 10, 11, 20, 21, 22) as float
 
-  // fused Mahalanobis: zero 4x4 with inverse((cov_B + delta cov_A delta^T).topLeft3x3) in the corner
-  // vgicp_impl:139-143 / gicp_impl:177-183
-  static void fused_mahalanobis(const Mat4& delta, const Mat4& cov_B, const Mat4& cov_A, Mat4& out) {
+  // 3x3 inverse((cov_B + delta cov_A delta^T).topLeft3x3): vgicp_impl:139-143 / gicp_impl:177-183
+  static void fused_mahalanobis3(const Mat4& delta, const Mat4& cov_B, const Mat4& cov_A, double inv[3][3]) {
     const Mat4 dC = mul44(delta, cov_A);
     const Mat4 dCdT = mul44(dC, transpose44(delta));
-    double rcr[3][3], inv[3][3];
+    double rcr[3][3];
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) rcr[r][c] = cov_B(r, c) + dCdT(r, c);
     inverse3(rcr, inv);
+  }
+  static void fused_mahalanobis(const Mat4& delta, const Mat4& cov_B, const Mat4& cov_A, Mat4& out) {
+    double inv[3][3];
+    fused_mahalanobis3(delta, cov_B, cov_A, inv);
     out.set_zero();
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) out(r, c) = inv[r][c];
+  }
+  // compact_cov / uncompact_cov (util/compact.hpp:9-25)
+  static Compact6 compact_cov(const double m[3][3]) {
+    return Compact6{{static_cast<float>(m[0][0]), static_cast<float>(m[1][0]), static_cast<float>(m[1][1]), static_cast<float>(m[2][0]), static_cast<float>(m[2][1]),
+                     static_cast<float>(m[2][2])}};
+  }
+  static void uncompact_cov(const Compact6& c, Mat4& out) {
+    out.set_zero();
+    out(0, 0) = c.v[0];
+    out(1, 0) = out(0, 1) = c.v[1];
+    out(1, 1) = c.v[2];
+    out(2, 0) = out(0, 2) = c.v[3];
+    out(2, 1) = out(1, 2) = c.v[4];
+    out(2, 2) = c.v[5];
+  }
+  void resize_caches(size_t N) {
+    if (cache_mode == 0) mahalanobis_full.resize(N);
+    if (cache_mode == 1) mahalanobis_compact.resize(N);
+  }
+  // the cache entry of point i (both factor families: vgicp_impl:131-163, gicp_impl:174-199)
+  void store_mahalanobis(size_t i, bool valid, const Mat4& delta, const Mat4* cov_B) {
+    if (cache_mode == 0) {
+      if (!valid)
+        mahalanobis_full[i].set_zero();
+      else
+        fused_mahalanobis(delta, *cov_B, source->covs[i], mahalanobis_full[i]);
+    } else if (cache_mode == 1) {
+      if (!valid) {
+        mahalanobis_compact[i] = Compact6{{0, 0, 0, 0, 0, 0}};
+      } else {
+        double inv[3][3];
+        fused_mahalanobis3(delta, *cov_B, source->covs[i], inv);
+        mahalanobis_compact[i] = compact_cov(inv);
+      }
+    }
+  }
+
+  // Eigen::AngleAxisd(R).angle() as Eigen computes it (Geometry/AngleAxis.h: via Quaternion(R), angle = 2 atan2(|vec|, |w|))
+  static double rotation_angle(const Mat4& T) {
+    const double m00 = T(0, 0), m11 = T(1, 1), m22 = T(2, 2);
+    double w, x, y, z;
+    const double t = m00 + m11 + m22;
+    if (t > 0.0) {
+      double tt = std::sqrt(t + 1.0);
+      w = 0.5 * tt;
+      tt = 0.5 / tt;
+      x = (T(2, 1) - T(1, 2)) * tt;
+      y = (T(0, 2) - T(2, 0)) * tt;
+      z = (T(1, 0) - T(0, 1)) * tt;
+    } else {
+      int i = 0;
+      if (m11 > m00) i = 1;
+      if (m22 > T(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      double tt = std::sqrt(T(i, i) - T(j, j) - T(k, k) + 1.0);
+      double q[3];
+      q[i] = 0.5 * tt;
+      tt = 0.5 / tt;
+      w = (T(k, j) - T(j, k)) * tt;
+      q[j] = (T(j, i) + T(i, j)) * tt;
+      q[k] = (T(k, i) + T(i, k)) * tt;
+      x = q[0], y = q[1], z = q[2];
+    }
+    const double n = std::sqrt(x * x + y * y + z * z);
+    return n != 0.0 ? 2.0 * std::atan2(n, std::fabs(w)) : 0.0;
+  }
+  static Mat4 rigid_inverse(const Mat4& T) {
+    Mat4 inv;
+    inv.set_zero();
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) inv(r, c) = T(c, r);
+    for (int r = 0; r < 3; r++) inv(r, 3) = -(inv(r, 0) * T(0, 3) + inv(r, 1) * T(1, 3) + inv(r, 2) * T(2, 3));
+    inv(3, 3) = 1.0;
+    return inv;
+  }
+  // gicp_impl:135-147 / icp_impl:132-140: skip re-association when the pose moved less than the tolerances
+  bool want_correspondence_update(const Mat4& delta) const {
+    if (corr_indices.size() == source->size() && (correspondence_update_tolerance_trans > 0.0 || correspondence_update_tolerance_rot > 0.0)) {
+      const Mat4 diff = mul44(rigid_inverse(delta), last_correspondence_point);
+      const double diff_rot = rotation_angle(diff);
+      const double diff_trans = std::sqrt(diff(0, 3) * diff(0, 3) + diff(1, 3) * diff(1, 3) + diff(2, 3) * diff(2, 3));
+      if (diff_rot < correspondence_update_tolerance_rot && diff_trans < correspondence_update_tolerance_trans) return false;
+    }
+    return true;
   }
 
   // vgicp_impl:99-172
@@ -547,7 +644,7 @@ struct orc_factor {
     linearization_point = delta;
     const int N = static_cast<int>(source->size());
     corr_voxels.resize(N);
-    mahalanobis_full.resize(N);
+    resize_caches(N);
 
 #pragma omp parallel for num_threads(num_threads) schedule(guided, 8)
     for (int i = 0; i < N; i++) {
@@ -556,41 +653,58 @@ struct orc_factor {
       const int voxel_id = target_voxels->lookup_voxel_index(coord);
       if (voxel_id < 0) {
         corr_voxels[i] = nullptr;
-        mahalanobis_full[i].set_zero();
+        store_mahalanobis(i, false, delta, nullptr);
       } else {
         const GaussianVoxel* voxel = &target_voxels->lookup_voxel(voxel_id);
         corr_voxels[i] = voxel;
-        fused_mahalanobis(delta, voxel->cov, source->covs[i], mahalanobis_full[i]);
+        store_mahalanobis(i, true, delta, &voxel->cov);
       }
     }
   }
 
-  // gicp_impl:132-215 (correspondence_update_tolerance_* at their default 0 => always update)
+  // gicp_impl:132-215
   void update_correspondences_gicp(const Mat4& delta) {
     linearization_point = delta;
+    const bool do_update = want_correspondence_update(delta);
+    if (do_update) last_correspondence_point = delta;
     const int N = static_cast<int>(source->size());
     corr_indices.resize(N);
-    mahalanobis_full.resize(N);
+    resize_caches(N);
 
+#pragma omp parallel for num_threads(num_threads) schedule(guided, 8)
+    for (int i = 0; i < N; i++) {
+      if (do_update) {
+        const Vec4 pt = transform_point(delta, source->points[i]);
+        size_t k_index = static_cast<size_t>(-1);
+        double k_sq_dist = -1;
+        const size_t num_found = target_tree->knn_search(pt.v, 1, &k_index, &k_sq_dist, max_correspondence_distance_sq);
+        corr_indices[i] = (num_found && k_sq_dist < max_correspondence_distance_sq) ? static_cast<long>(k_index) : -1;
+      }
+      store_mahalanobis(i, corr_indices[i] >= 0, delta, corr_indices[i] >= 0 ? &target->covs[corr_indices[i]] : nullptr);
+    }
+  }
+
+  // icp_impl:131-182 (no Mahalanobis cache; the tolerance check returns before anything is touched)
+  void update_correspondences_icp(const Mat4& delta) {
+    if (!want_correspondence_update(delta)) return;
+    last_correspondence_point = delta;
+    const int N = static_cast<int>(source->size());
+    corr_indices.resize(N);
 #pragma omp parallel for num_threads(num_threads) schedule(guided, 8)
     for (int i = 0; i < N; i++) {
       const Vec4 pt = transform_point(delta, source->points[i]);
       size_t k_index = static_cast<size_t>(-1);
       double k_sq_dist = -1;
       const size_t num_found = target_tree->knn_search(pt.v, 1, &k_index, &k_sq_dist, max_correspondence_distance_sq);
-      corr_indices[i] = (num_found && k_sq_dist < max_correspondence_distance_sq) ? static_cast<long>(k_index) : -1;
-
-      if (corr_indices[i] < 0) {
-        mahalanobis_full[i].set_zero();
-      } else {
-        fused_mahalanobis(delta, target->covs[corr_indices[i]], source->covs[i], mahalanobis_full[i]);
-      }
+      corr_indices[i] = (num_found == 0 || k_sq_dist > max_correspondence_distance_sq) ? -1 : static_cast<long>(k_index);
     }
   }
 
   void update_correspondences(const Mat4& delta) {
     if (is_vgicp)
       update_correspondences_vgicp(delta);
+    else if (icp_mode)
+      update_correspondences_icp(delta);
     else
       update_correspondences_gicp(delta);
   }
@@ -617,7 +731,26 @@ struct orc_factor {
       Vec4 residual;
       for (int k = 0; k < 4; k++) residual[k] = (*mean_B)[k] - transed_mean_A[k];
 
-      const Mat4& mahalanobis = mahalanobis_full[i];
+      // vgicp_impl:209-224 / gicp_impl:252-266: the cached, uncompacted or (NONE) re-derived fused Mahalanobis matrix
+      Mat4 mahalanobis;
+      const Vec4* normal_B = nullptr;
+      if (icp_mode) {
+        // icp_impl:205-248: residual^T residual, J^T J -- written as M = I; point-to-plane scales residual and the Jacobian
+        // rows by the target normal (normal_B.array() * residual.array(), normal_B.asDiagonal() * J)
+        mahalanobis.set_zero();
+        for (int k = 0; k < 4; k++) mahalanobis(k, k) = 1.0;
+        if (icp_mode == 2) {
+          normal_B = &target->normals[corr_indices[i]];
+          for (int k = 0; k < 4; k++) residual[k] = (*normal_B)[k] * residual[k];
+        }
+      } else if (cache_mode == 0) {
+        mahalanobis = mahalanobis_full[i];
+      } else if (cache_mode == 1) {
+        uncompact_cov(mahalanobis_compact[i], mahalanobis);
+      } else {
+        const Mat4& cov_B = is_vgicp ? corr_voxels[i]->cov : target->covs[corr_indices[i]];
+        fused_mahalanobis(linearization_point, cov_B, source->covs[i], mahalanobis);
+      }
 
       // error = residual^T * mahalanobis * residual
       double Mr[4];
@@ -647,6 +780,13 @@ struct orc_factor {
           J_source(r, 3 + c) = -delta(r, c);
         }
         J_target(r, 3 + r) = 1.0;
+      }
+      if (normal_B) {
+        for (int r = 0; r < 4; r++)
+          for (int c = 0; c < 6; c++) {
+            J_target(r, c) = (*normal_B)[r] * J_target(r, c);
+            J_source(r, c) = (*normal_B)[r] * J_source(r, c);
+          }
       }
 
       // J^T * mahalanobis (6x4)
@@ -906,6 +1046,198 @@ orc_factor* orc_gicp_create(const orc_cloud* target, const orc_kdtree* tree, con
   f->source = source;
   return f;
 }
+// integrated_icp_factor_impl.hpp:20-52: point-to-point (use_point_to_plane = 0) or point-to-plane ICP over the same kd-tree
+orc_factor* orc_icp_create(const orc_cloud* target, const orc_kdtree* tree, const orc_cloud* source, int use_point_to_plane) {
+  if (use_point_to_plane && !target->has_normals()) {
+    std::fprintf(stderr, "error: target frame doesn't have required attributes for icp\n");  // icp_impl:37-40
+    std::abort();
+  }
+  auto* f = new orc_factor;
+  f->is_vgicp = false;
+  f->icp_mode = use_point_to_plane ? 2 : 1;
+  f->target = target;
+  f->target_tree = tree;
+  f->source = source;
+  return f;
+}
+void orc_cloud_set_normals(orc_cloud* c, const double* nxyz) {
+  c->normals.resize(c->size());
+  for (size_t i = 0; i < c->size(); i++) c->normals[i] = Vec4{{nxyz[i * 3], nxyz[i * 3 + 1], nxyz[i * 3 + 2], 0.0}};
+}
+void orc_factor_set_fused_cov_cache_mode(orc_factor* f, int mode) { f->cache_mode = mode; }  // integrated_gicp_factor.hpp:104-105
+void orc_factor_set_correspondence_update_tolerance(orc_factor* f, double angle, double trans) {  // integrated_gicp_factor.hpp:106-109
+  f->correspondence_update_tolerance_rot = angle;
+  f->correspondence_update_tolerance_trans = trans;
+}
+
+// src/gtsam_points/types/gaussian_voxelmap_cpu_funcs.cpp:126-143 / :145-173
+double orc_overlap(const orc_voxelmap* target, const orc_cloud* source, const double* T_rm16) {
+  const Mat4 T = from_rm16(T_rm16);
+  int num_overlap = 0;
+  for (size_t i = 0; i < source->size(); i++) {
+    const Vec4 pt = transform_point(T, source->points[i]);
+    if (target->lookup_voxel_index(target->voxel_coord(pt)) >= 0) num_overlap++;
+  }
+  return static_cast<double>(num_overlap) / source->size();
+}
+double orc_overlap_multi(const orc_voxelmap* const* targets, int num_targets, const orc_cloud* source, const double* Ts_rm16) {
+  int num_overlap = 0;
+  for (size_t i = 0; i < source->size(); i++) {
+    for (int j = 0; j < num_targets; j++) {
+      const Mat4 T = from_rm16(Ts_rm16 + 16 * j);
+      const Vec4 pt = transform_point(T, source->points[i]);
+      if (targets[j]->lookup_voxel_index(targets[j]->voxel_coord(pt)) >= 0) {
+        num_overlap++;
+        break;
+      }
+    }
+  }
+  return static_cast<double>(num_overlap) / source->size();
+}
+
+// GaussianVoxelData (types/gaussian_voxel_data.hpp:11-54): 56-byte packed record {coord int32 x3, num_points int32, mean float x3,
+// cov float x6 (00, 01, 02, 11, 12, 22), intensity float}; save_compact / load: src/.../gaussian_voxelmap_cpu.cpp:79-135
+namespace {
+struct GaussianVoxelData {
+  int32_t coord[3];
+  int32_t num_points;
+  float mean[3];
+  float cov[6];
+  float intensity;
+};
+static_assert(sizeof(GaussianVoxelData) == 56, "GaussianVoxelData is 56 bytes in the reference");
+}  // namespace
+int orc_voxelmap_save_compact(const orc_voxelmap* v, const char* path) {
+  std::vector<GaussianVoxelData> serial(v->flat_voxels.size());
+  for (size_t i = 0; i < serial.size(); i++) {
+    const auto& e = *v->flat_voxels[i];
+    GaussianVoxelData& d = serial[i];
+    d.coord[0] = e.first.coord.x, d.coord[1] = e.first.coord.y, d.coord[2] = e.first.coord.z;
+    d.num_points = static_cast<int32_t>(e.second.num_points);
+    for (int k = 0; k < 3; k++) d.mean[k] = static_cast<float>(e.second.mean[k]);
+    const Mat4& c = e.second.cov;
+    d.cov[0] = static_cast<float>(c(0, 0)), d.cov[1] = static_cast<float>(c(0, 1)), d.cov[2] = static_cast<float>(c(0, 2));
+    d.cov[3] = static_cast<float>(c(1, 1)), d.cov[4] = static_cast<float>(c(1, 2)), d.cov[5] = static_cast<float>(c(2, 2));
+    d.intensity = static_cast<float>(e.second.intensity);
+  }
+  std::FILE* fp = std::fopen(path, "wb");
+  if (!fp) return -1;
+  // operator<< of a double prints with 6 significant digits (%g), like the reference's ofstream
+  std::fprintf(fp, "compact 1\nresolution %g\nlru_count %zu\nlru_cycle %zu\nlru_thresh %zu\nvoxel_bytes %zu\nnum_voxels %zu\n", 1.0 / v->inv_leaf_size, v->lru_counter,
+               v->lru_clear_cycle, v->lru_horizon, sizeof(GaussianVoxelData), serial.size());
+  std::fwrite(serial.data(), sizeof(GaussianVoxelData), serial.size(), fp);
+  std::fclose(fp);
+  return 0;
+}
+orc_voxelmap* orc_voxelmap_load(const char* path) {
+  std::FILE* fp = std::fopen(path, "rb");
+  if (!fp) return nullptr;
+  char tok[64];
+  int compact = 0;
+  double resolution = 1.0;
+  size_t lru_count = 0, lru_cycle = 0, lru_thresh = 0, voxel_bytes = 0, num_voxels = 0;
+  if (std::fscanf(fp, "%63s %d %63s %lf %63s %zu %63s %zu %63s %zu %63s %zu %63s %zu", tok, &compact, tok, &resolution, tok, &lru_count, tok, &lru_cycle, tok, &lru_thresh, tok,
+                  &voxel_bytes, tok, &num_voxels) != 14 ||
+      voxel_bytes != sizeof(GaussianVoxelData)) {
+    std::fclose(fp);
+    return nullptr;
+  }
+  int ch;
+  while ((ch = std::fgetc(fp)) != EOF && ch != '\n') {
+  }
+  std::vector<GaussianVoxelData> serial(num_voxels);
+  const size_t got = std::fread(serial.data(), sizeof(GaussianVoxelData), num_voxels, fp);
+  std::fclose(fp);
+  if (got != num_voxels) return nullptr;
+  auto* v = new orc_voxelmap(resolution);
+  v->lru_counter = lru_count, v->lru_clear_cycle = lru_cycle, v->lru_horizon = lru_thresh;
+  for (const auto& d : serial) {  // GaussianVoxelData::uncompact (gaussian_voxel_data.hpp:27-46)
+    auto e = std::make_shared<std::pair<VoxelInfo, GaussianVoxel>>();
+    e->first.lru = 0;
+    e->first.coord = Vec3i{d.coord[0], d.coord[1], d.coord[2]};
+    GaussianVoxel& g = e->second;
+    g.finalized = true;
+    g.num_points = static_cast<size_t>(d.num_points);
+    g.mean = Vec4{{d.mean[0], d.mean[1], d.mean[2], 1.0}};
+    g.cov.set_zero();
+    g.cov(0, 0) = d.cov[0];
+    g.cov(0, 1) = g.cov(1, 0) = d.cov[1];
+    g.cov(0, 2) = g.cov(2, 0) = d.cov[2];
+    g.cov(1, 1) = d.cov[3];
+    g.cov(1, 2) = g.cov(2, 1) = d.cov[4];
+    g.cov(2, 2) = d.cov[5];
+    g.intensity = d.intensity;
+    v->flat_voxels.emplace_back(e);
+    v->voxels[e->first.coord] = v->flat_voxels.size() - 1;
+  }
+  return v;
+}
+
+// merge_frames (src/gtsam_points/types/gaussian_voxelmap_cpu_funcs.cpp:25-113): 21-bit voxel keys relative to the FIRST pose,
+// sorted (std::sort is not stable, but every point of a voxel receives the same destination, so the result does not depend on
+// the order inside a key), sums taken in WORLD coordinates (poses[i], not relative) in frame / point order, divided by the
+// count (the homogeneous w).  Returns the number of merged points; out_* sized by the caller for the total point count.
+size_t orc_merge_frames(const double* poses_rm16, const orc_cloud* const* frames, int num_frames, double downsample_resolution, double* out_xyz, double* out_cov3x3) {
+  constexpr int coord_bits = 21;
+  constexpr uint64_t coord_bitmask = (1ull << coord_bits) - 1;
+  const int coord_offset = 1 << (coord_bits - 1);
+  const double inv_resolution = 1.0 / downsample_resolution;
+  std::vector<std::pair<uint64_t, uint64_t>> coords_indices;
+  const Mat4 first_inv = orc_factor::rigid_inverse(from_rm16(poses_rm16));
+  for (int fid = 0; fid < num_frames; fid++) {
+    const Mat4 pose = mul44(first_inv, from_rm16(poses_rm16 + 16 * fid));
+    for (size_t pid = 0; pid < frames[fid]->size(); pid++) {
+      const Vec4 point = transform_point(pose, frames[fid]->points[pid]);
+      int64_t c[3];
+      bool out_of_range = false;
+      for (int k = 0; k < 3; k++) {
+        c[k] = static_cast<int64_t>(fast_floor1(point[k] * inv_resolution)) + coord_offset;
+        // the reference compares a signed Array4i against the unsigned mask: negative values convert to huge unsigned ones
+        if (c[k] < 0 || static_cast<uint64_t>(c[k]) > coord_bitmask) out_of_range = true;
+      }
+      if (out_of_range) continue;
+      const uint64_t index = (static_cast<uint64_t>(fid) << 32) | (static_cast<uint64_t>(pid) & 0xffffffffull);
+      coords_indices.emplace_back((static_cast<uint64_t>(c[0]) & coord_bitmask) | ((static_cast<uint64_t>(c[1]) & coord_bitmask) << coord_bits) |
+                                    ((static_cast<uint64_t>(c[2]) & coord_bitmask) << (2 * coord_bits)),
+                                  index);
+    }
+  }
+  std::sort(coords_indices.begin(), coords_indices.end(), [](const auto& l, const auto& r) { return l.first < r.first; });
+  std::vector<std::vector<size_t>> dest(num_frames);
+  for (int i = 0; i < num_frames; i++) dest[i].assign(frames[i]->size(), 0);
+  size_t num_voxels = 0;
+  for (size_t i = 0; i < coords_indices.size(); i++) {
+    if (i && coords_indices[i - 1].first != coords_indices[i].first) num_voxels++;
+    const uint64_t index = coords_indices[i].second;
+    dest[(index >> 32) & 0xffffffffull][index & 0xffffffffull] = num_voxels;
+  }
+  num_voxels++;
+  std::vector<Vec4> pts(num_voxels, Vec4{{0, 0, 0, 0}});
+  Mat4 zero;
+  zero.set_zero();
+  std::vector<Mat4> covs(num_voxels, zero);
+  for (int i = 0; i < num_frames; i++) {
+    const Mat4 pose = from_rm16(poses_rm16 + 16 * i);
+    const Mat4 poseT = transpose44(pose);
+    for (size_t j = 0; j < frames[i]->size(); j++) {
+      const size_t d = dest[i][j];
+      const Vec4 tp = transform_point(pose, frames[i]->points[j]);
+      for (int k = 0; k < 4; k++) pts[d][k] += tp[k];
+      const Mat4 c = mul44(mul44(pose, frames[i]->covs[j]), poseT);
+      for (int k = 0; k < 16; k++) covs[d].m[k] += c.m[k];
+    }
+  }
+  for (size_t i = 0; i < num_voxels; i++) {
+    const double w = pts[i][3];
+    for (int k = 0; k < 16; k++) covs[i].m[k] /= w;
+    for (int k = 0; k < 4; k++) pts[i][k] /= w;
+    for (int k = 0; k < 3; k++) out_xyz[i * 3 + k] = pts[i][k];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) out_cov3x3[i * 9 + r * 3 + c] = covs[i](r, c);
+  }
+  return num_voxels;
+}
+
 void orc_factor_destroy(orc_factor* f) { delete f; }
 void orc_factor_set_num_threads(orc_factor* f, int n) { f->num_threads = n < 1 ? 1 : n; }
 void orc_factor_set_max_correspondence_distance(orc_factor* f, double dist) { f->max_correspondence_distance_sq = dist * dist; }

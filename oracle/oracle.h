@@ -73,6 +73,22 @@ void orc_estimate_covariances(const orc_cloud* cloud, int k_neighbors, const dou
 /* IntegratedVGICPFactor_ / IntegratedGICPFactor_ in FusedCovCacheMode::FULL */
 orc_factor* orc_vgicp_create(const orc_voxelmap* target, const orc_cloud* source);
 orc_factor* orc_gicp_create(const orc_cloud* target, const orc_kdtree* tree, const orc_cloud* source);
+/* IntegratedICPFactor_ (include/gtsam_points/factors/impl/integrated_icp_factor_impl.hpp:131-248); point-to-plane needs
+ * target normals (orc_cloud_set_normals, n x 3) */
+orc_factor* orc_icp_create(const orc_cloud* target, const orc_kdtree* tree, const orc_cloud* source, int use_point_to_plane);
+void orc_cloud_set_normals(orc_cloud*, const double* nxyz);
+/* FusedCovCacheMode 0 FULL / 1 COMPACT / 2 NONE (integrated_gicp_factor.hpp:20-24,104-105) */
+void orc_factor_set_fused_cov_cache_mode(orc_factor*, int mode);
+/* integrated_gicp_factor.hpp:106-109, impl:135-147 */
+void orc_factor_set_correspondence_update_tolerance(orc_factor*, double angle, double trans);
+/* overlap (src/gtsam_points/types/gaussian_voxelmap_cpu_funcs.cpp:126-173) */
+double orc_overlap(const orc_voxelmap* target, const orc_cloud* source, const double* T_target_source_rm16);
+double orc_overlap_multi(const orc_voxelmap* const* targets, int num_targets, const orc_cloud* source, const double* Ts_rm16);
+/* save_compact / load (src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:79-135, types/gaussian_voxel_data.hpp:11-54) */
+int orc_voxelmap_save_compact(const orc_voxelmap*, const char* path);
+orc_voxelmap* orc_voxelmap_load(const char* path);
+/* merge_frames (gaussian_voxelmap_cpu_funcs.cpp:25-113); out arrays sized for the total number of input points */
+size_t orc_merge_frames(const double* poses_rm16, const orc_cloud* const* frames, int num_frames, double downsample_resolution, double* out_xyz, double* out_cov3x3);
 void orc_factor_destroy(orc_factor*);
 void orc_factor_set_num_threads(orc_factor*, int n);
 void orc_factor_set_max_correspondence_distance(orc_factor*, double dist); /* GICP only */

@@ -17,6 +17,10 @@ LINEARIZED_DOUBLES = 122
 
 
 def build(force=False):
+    if os.environ.get("B2_ORACLE_NATIVE") == "1":
+        # secondary CPU number of bench.py: the same code with -march=native, ALWAYS rebuilt on the host that runs it
+        subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle_native.so"], stdout=subprocess.DEVNULL)
+        return os.path.join(ORACLE_DIR, "liboracle_native.so")
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
@@ -61,6 +65,21 @@ def lib():
         L.orc_factor_correspondences.argtypes = [vp, lp]
         L.orc_calc_delta.argtypes = [dp, dp, dp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_icp_create.restype = vp
+        L.orc_icp_create.argtypes = [vp, vp, vp, C.c_int]
+        L.orc_cloud_set_normals.argtypes = [vp, dp]
+        L.orc_factor_set_fused_cov_cache_mode.argtypes = [vp, C.c_int]
+        L.orc_factor_set_correspondence_update_tolerance.argtypes = [vp, C.c_double, C.c_double]
+        L.orc_overlap.restype = C.c_double
+        L.orc_overlap.argtypes = [vp, vp, dp]
+        L.orc_overlap_multi.restype = C.c_double
+        L.orc_overlap_multi.argtypes = [C.POINTER(vp), C.c_int, vp, dp]
+        L.orc_voxelmap_save_compact.restype = C.c_int
+        L.orc_voxelmap_save_compact.argtypes = [vp, C.c_char_p]
+        L.orc_voxelmap_load.restype = vp
+        L.orc_voxelmap_load.argtypes = [C.c_char_p]
+        L.orc_merge_frames.restype = C.c_size_t
+        L.orc_merge_frames.argtypes = [dp, C.POINTER(vp), C.c_int, C.c_double, dp, dp]
         _LIB = L
     return _LIB
 
@@ -90,6 +109,10 @@ class Cloud:
         dummy = np.zeros(1)  # keep the pointers non-NULL for empty clouds
         self.h = lib().orc_cloud_create(_dp(self.pts) if self.n else _dp(dummy), None if self.covs is None else (_dp(self.covs) if self.n else _dp(dummy)), self.n)
 
+    def set_normals(self, normals):
+        self.normals = np.ascontiguousarray(normals, dtype=np.float64).reshape(self.n, 3)
+        lib().orc_cloud_set_normals(self.h, _dp(self.normals))
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_cloud_destroy(self.h)
@@ -97,13 +120,32 @@ class Cloud:
 
 
 class VoxelMap:
-    def __init__(self, resolution):
+    def __init__(self, resolution, _handle=None):
         self.resolution = resolution
-        self.h = lib().orc_voxelmap_create(resolution)
+        self.h = _handle if _handle is not None else lib().orc_voxelmap_create(resolution)
         self._clouds = []
 
     def insert(self, cloud: Cloud):
         lib().orc_voxelmap_insert(self.h, cloud.h)
+
+    def set_lru(self, horizon, clear_cycle):
+        lib().orc_voxelmap_set_lru(self.h, int(horizon), int(clear_cycle))
+
+    def overlap(self, source: Cloud, T_target_source) -> float:
+        T = np.ascontiguousarray(T_target_source, dtype=np.float64).reshape(16)
+        return lib().orc_overlap(self.h, source.h, _dp(T))
+
+    def save_compact(self, path):
+        if lib().orc_voxelmap_save_compact(self.h, str(path).encode()) != 0:
+            raise IOError(path)
+
+    @staticmethod
+    def load(path):
+        h = lib().orc_voxelmap_load(str(path).encode())
+        if not h:
+            raise IOError(path)
+        vm = VoxelMap(1.0, _handle=h)
+        return vm
 
     @property
     def num_voxels(self):
@@ -139,6 +181,21 @@ def estimate_covariances(points, k_neighbors=10, eigen_values=(1e-3, 1.0, 1.0), 
     return out
 
 
+def overlap_multi(targets, source: Cloud, Ts_target_source) -> float:
+    Ts = np.ascontiguousarray(Ts_target_source, dtype=np.float64).reshape(len(targets), 16)
+    arr = (C.c_void_p * len(targets))(*[t.h for t in targets])
+    return lib().orc_overlap_multi(arr, len(targets), source.h, _dp(Ts))
+
+
+def merge_frames(poses, frames, resolution):
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(len(frames), 16)
+    total = sum(f.n for f in frames)
+    xyz, cov = np.zeros((total, 3)), np.zeros((total, 3, 3))
+    arr = (C.c_void_p * len(frames))(*[f.h for f in frames])
+    m = lib().orc_merge_frames(_dp(poses), arr, len(frames), float(resolution), _dp(xyz), _dp(cov))
+    return xyz[:m].copy(), cov[:m].copy()
+
+
 class KdTree:
     def __init__(self, cloud: Cloud, num_threads=1):
         self.cloud = cloud
@@ -167,13 +224,24 @@ class KdTree:
 class Factor:
     """IntegratedVGICPFactor (target = VoxelMap) or IntegratedGICPFactor (target = Cloud + KdTree)."""
 
-    def __init__(self, target, source: Cloud, tree: KdTree = None, num_threads=1):
+    FULL, COMPACT, NONE = 0, 1, 2
+
+    def __init__(self, target, source: Cloud, tree: KdTree = None, num_threads=1, icp=None):
+        """icp: None (GICP / VGICP), "point" (IntegratedICPFactor) or "plane" (IntegratedPointToPlaneICPFactor)."""
         self.target, self.source, self.tree = target, source, tree
         if isinstance(target, VoxelMap):
             self.h = lib().orc_vgicp_create(target.h, source.h)
+        elif icp:
+            self.h = lib().orc_icp_create(target.h, tree.h, source.h, 1 if icp == "plane" else 0)
         else:
             self.h = lib().orc_gicp_create(target.h, tree.h, source.h)
         lib().orc_factor_set_num_threads(self.h, num_threads)
+
+    def set_fused_cov_cache_mode(self, mode):
+        lib().orc_factor_set_fused_cov_cache_mode(self.h, int(mode))
+
+    def set_correspondence_update_tolerance(self, angle, trans):
+        lib().orc_factor_set_correspondence_update_tolerance(self.h, float(angle), float(trans))
 
     def set_num_threads(self, n):
         lib().orc_factor_set_num_threads(self.h, n)
