@@ -48,18 +48,31 @@ SIGNATURES = {
     "b2_ctx_destroy": (C.c_int, [_vp]),
     "b2_ctx_synchronize": (C.c_int, [_vp]),
     "b2_ctx_stream": (_vp, [_vp]),
+    "b2_device_malloc": (C.c_int, [_vp, C.c_size_t, _pp]),
+    "b2_device_free": (C.c_int, [_vp, _vp]),
+    "b2_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "b2_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "b2_cloud_create": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_size_t, C.c_uint, _pp]),
     "b2_cloud_destroy": (C.c_int, [_vp]),
     "b2_cloud_get_info": (C.c_int, [_vp, C.POINTER(CloudInfo)]),
     "b2_voxelmap_create_from_points": (C.c_int, [_vp, C.c_double, _dp, C.c_int, _dp, C.c_int, C.c_size_t, _pp]),
+    "b2_voxelmap_create": (C.c_int, [_vp, C.c_double, _pp]),
+    "b2_voxelmap_set_lru": (C.c_int, [_vp, C.c_size_t, C.c_size_t]),
+    "b2_voxelmap_insert": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_size_t]),
     "b2_voxelmap_create_from_voxels": (C.c_int, [_vp, C.c_double, _ip, _dp, _dp, _ip, C.c_size_t, _pp]),
     "b2_voxelmap_destroy": (C.c_int, [_vp]),
     "b2_voxelmap_get_info": (C.c_int, [_vp, C.POINTER(VoxelMapInfo)]),
     "b2_voxelmap_download": (C.c_int, [_vp, _ip, _dp, _dp, _ip]),
+    "b2_voxelmap_save_compact": (C.c_int, [_vp, C.c_char_p]),
+    "b2_voxelmap_load": (C.c_int, [_vp, C.c_char_p, _pp]),
+    "b2_overlap": (C.c_int, [_pp, C.c_size_t, _vp, _dp, _dp]),
     "b2_voxelmap_lookup": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, _ip]),
     "b2_kdtree_create": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, _pp]),
     "b2_kdtree_destroy": (C.c_int, [_vp]),
     "b2_kdtree_knn1": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, C.c_double, _lp, _dp]),
+    "b2_kdtree_knn": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, C.c_int, C.c_double, _lp, _dp]),
+    "b2_estimate_covariances": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, C.c_int, _dp, _dp]),
+    "b2_kdtree_estimate_covariances": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "b2_vgicp_factor_create": (C.c_int, [_vp, _vp, _vp, _pp]),
     "b2_gicp_factor_create": (C.c_int, [_vp, _vp, _vp, _vp, _pp]),
     "b2_factor_destroy": (C.c_int, [_vp]),
@@ -68,6 +81,9 @@ SIGNATURES = {
     "b2_factor_correspondences": (C.c_int, [_vp, _lp]),
     "b2_factor_linearize": (C.c_int, [_vp, _dp, _dp]),
     "b2_factor_error": (C.c_int, [_vp, _dp, _dp]),
+    "b2_factor_issue_linearize": (C.c_int, [_vp, _dp, _vp]),
+    "b2_factor_issue_error": (C.c_int, [_vp, _dp, _vp]),
+    "b2_factor_sync": (C.c_int, [_vp]),
     "b2_factor_set_create": (C.c_int, [_vp, _pp, C.c_size_t, _pp]),
     "b2_factor_set_destroy": (C.c_int, [_vp]),
     "b2_factor_set_size": (C.c_size_t, [_vp]),

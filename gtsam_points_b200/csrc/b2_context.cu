@@ -128,4 +128,37 @@ b2_status b2_ctx_synchronize(b2_ctx* ctx) {
 
 void* b2_ctx_stream(b2_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 
+b2_status b2_device_malloc(b2_ctx* ctx, size_t bytes, void** out) {
+  B2_REQUIRE(ctx && out, "b2_device_malloc: NULL argument");
+  *out = nullptr;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return B2_OK;
+}
+
+b2_status b2_device_free(b2_ctx* ctx, void* ptr) {
+  B2_REQUIRE(ctx != nullptr, "b2_device_free: ctx is NULL");
+  if (!ptr) return B2_OK;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaFree(ptr));
+  return B2_OK;
+}
+
+b2_status b2_memcpy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  B2_REQUIRE(ctx && (bytes == 0 || (dst && src)), "b2_memcpy_d2h: NULL argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B2_OK;
+}
+
+b2_status b2_memcpy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  B2_REQUIRE(ctx && (bytes == 0 || (dst && src)), "b2_memcpy_h2d: NULL argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B2_OK;
+}
+
 }  // extern "C"

@@ -6,11 +6,13 @@
 // coordinates and the bucket group; accumulate warps: 11 gathers in front of every batch).  This form takes every byte
 // that CAN be known ahead of time off the scoreboards:
 //   * the STREAMS (3 coordinate planes, 6 covariance planes, the frozen correspondences in error mode: 94 % of the bytes)
-//     arrive through the TMA unit: per probe warp, one elected lane issues 1-D bulk copies (cp.async.bulk, 256-512 B per
-//     plane and 64-point warp tile) into a small multi-stage shared-memory ring, completion on an mbarrier
-//     (complete_tx::bytes).  Coordinates are staged kSX - 1 tiles ahead, covariances kLC tiles ahead and RETAINED until
-//     the accumulate warp has consumed every hit of the tile (it reads the covariance of a hit from the stage by its
-//     tile-local index -- hits travel through the ring as 32-byte items (R p, stage slot, target id) as before).
+//     arrive through the TMA unit: two dedicated PRODUCER warps (one lane each; one for the coordinate stream, one for the
+//     covariance stream) issue 1-D bulk copies (cp.async.bulk, one per plane and CTA tile of kTile = 512 points: 2-4 KB
+//     each) into multi-stage shared-memory rings, completion on `full` mbarriers (complete_tx::bytes); stages are handed
+//     back through `empty` mbarriers on which every probe warp arrives once.  The probe warps never compute a global
+//     address for the streams.  A coordinate stage is released as soon as the probe warps have read it; a covariance
+//     stage is RETAINED until the accumulate warps have consumed every hit of the tile (they read the covariance of a hit
+//     from the stage by its tile-local index -- hits travel through the rings as 32-byte items (R p, stage slot, target id)).
 //   * the GATHERED target records (80 B per hit) are fetched by the accumulate warp for batch k + 1 with cp.async
 //     (LDGSTS, 5 x 16 B per lane) into a private double buffer while it computes batch k: the float64 arithmetic reads
 //     nothing but shared memory.
@@ -18,8 +20,8 @@
 //     (no registers, no shared-memory reads), and the kernel never touches host memory on its way in.
 // What stays on a scoreboard is the bucket group of the hash probe (data dependent address), 2 points per lane in flight.
 //
-// Stage retention and liveness.  A covariance stage is re-armed only after the accumulate warp's published `head` has
-// passed the last hit of the tile that used it (`tile_end`).  Because the accumulate warp takes batches of exactly 32
+// Stage retention and liveness.  A probe warp releases its share of a covariance stage only after its accumulate warp's
+// published `head` has passed the last hit of the tile that used it (`tile_end`).  Because the accumulate warp takes batches of exactly 32
 // consecutive hits, it could be waiting for hits that the probe warp cannot produce before the stage is free; in that case
 // (decided from hit counts alone, hence deterministic) the probe warp publishes a FORCED batch boundary `flush` = its
 // current tail: the accumulate warp then takes the shorter batch [head, flush).  Batch boundaries therefore depend only on
@@ -35,20 +37,27 @@ namespace B2_V2_NAMESPACE {
 
 constexpr int kP = B2_V2_PRODUCERS;
 constexpr int kC = B2_V2_CONSUMERS;
-constexpr int kThreads = (kP + kC) * 32;
+constexpr int kAux = 4;  // one more warpgroup: warp 0 = coordinate-stream producer, warp 1 = covariance-stream producer, 2-3 exit
+constexpr int kThreads = (kP + kC + kAux) * 32;
 constexpr int kPPL = B2_V2_PPL;          // points per probe lane and warp tile (independent chains interleaved for ILP)
 constexpr int kWarpPoints = 32 * kPPL;   // contiguous source points per probe warp and tile
 constexpr int kTile = kP * kWarpPoints;  // source points per CTA tile
 constexpr int kRing = B2_V2_RING;        // items per ring (power of two)
-constexpr int kSX = B2_V2_XYZ_STAGES;    // coordinate stages per probe warp (lookahead kSX - 1 tiles)
-constexpr int kSC = B2_V2_COV_STAGES;    // covariance stages per probe warp
-constexpr int kLC = B2_V2_COV_AHEAD;     // covariance lookahead in tiles (retention = kSC - kLC tiles after the tile is probed)
+constexpr int kSX = B2_V2_XYZ_STAGES;    // coordinate stages (CTA tiles in flight ahead of the probe warps)
+constexpr int kSC = B2_V2_COV_STAGES;    // covariance stages
+constexpr int kRet = B2_V2_COV_RETAIN;   // a probe warp releases the covariance stage of tile j when it starts tile j + kRet: lookahead kSC - kRet tiles
 constexpr int kRingsPerConsumer = kP / kC;
 constexpr uint32_t kBatch = 32u;
 static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
 static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
 static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 + kWarpPoints, "ring capacity: a tile's hits + a batch being read + a batch");
-static_assert(kSX >= 2 && kLC >= 1 && kSC > kLC, "stage counts");
+static_assert(kSX >= 2 && kRet >= 1 && kSC > kRet, "stage counts");
+// setmaxnreg moves registers inside the CTA's OWN pool (what the launch allocated: threads x the per-thread count the
+// launch bounds give); the SM's unallocated remainder is not available.  A split that asks for more deadlocks the
+// accumulate warps in USETMAXREG.TRY_ALLOC.
+constexpr int kLaunchRegs = ((65536 / kThreads) / 8) * 8 > 255 ? 248 : ((65536 / kThreads) / 8) * 8;
+static_assert(kP * B2_V2_REGS_PRODUCER + kC * B2_V2_REGS_CONSUMER + kAux * B2_V2_REGS_AUX <= (kP + kC + kAux) * kLaunchRegs, "register split exceeds the CTA's pool");
+static_assert(B2_V2_REGS_PRODUCER <= kLaunchRegs && B2_V2_REGS_AUX <= kLaunchRegs && B2_V2_REGS_CONSUMER >= kLaunchRegs, "dec / inc directions");
 
 constexpr unsigned kSpinLimit = 1u << 25;  // polls (with sleeps: >= 2 s) before a wait traps: a protocol bug must not hang the GPU
 
@@ -70,6 +79,16 @@ struct Backoff {
 };
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kC * 32) : "memory"); }
+
+#ifdef B2_V2_TIMING
+// development aid: per-warp cycle totals of the last launch: [block][warp][slot]
+__device__ unsigned long long g_warp_cycles[160 * 32 * 8];
+#define B2_T0(var) const long long var = clock64()
+#define B2_TACC(slot, var) tacc[slot] += clock64() - var
+#else
+#define B2_T0(var)
+#define B2_TACC(slot, var)
+#endif
 
 // ---- mbarrier / bulk-copy (TMA) / cp.async primitives ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -93,6 +112,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++polls > (1u << 22)) __trap();
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 // global -> shared bulk copy (SASS: UBLKCP), `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -106,18 +126,18 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ---- shared-memory layout ---------------------------------------------------------------------------------------------
-// dynamic part, per probe warp: [kSX coordinate stages | kSC covariance stages | ring], then per accumulate warp the
-// record double buffer.  Everything is a multiple of 128 bytes.
+// dynamic part: [kSX coordinate stages | kSC covariance stages] (CTA tiles), then one ring per probe warp, then per accumulate
+// warp the record double buffer.  Everything is a multiple of 128 bytes.
 constexpr uint32_t kRecBufBytes = 32u * kRecordDoubles * 8u;  // one batch of gathered target records
 template <typename PT, int MODE>
 struct XyzStage {
-  static constexpr uint32_t kPlane = kWarpPoints * sizeof(PT);
+  static constexpr uint32_t kPlane = kTile * sizeof(PT);
   static constexpr uint32_t kCorrOff = 3u * kPlane;
-  static constexpr uint32_t kBytes = 3u * kPlane + (MODE == MODE_ERROR ? kWarpPoints * 4u : 0u);
+  static constexpr uint32_t kBytes = 3u * kPlane + (MODE == MODE_ERROR ? kTile * 4u : 0u);
 };
 template <typename CT>
 struct CovStage {
-  static constexpr uint32_t kPlane = kWarpPoints * sizeof(CT);
+  static constexpr uint32_t kPlane = kTile * sizeof(CT);
   static constexpr uint32_t kBytes = 6u * kPlane;
 };
 constexpr uint32_t kRingBytes1 = 2u * kRing * 16u;
@@ -126,10 +146,9 @@ struct Layout {
   static constexpr uint32_t kXyzOff = 0u;
   static constexpr uint32_t kCovOff = kSX * XyzStage<PT, MODE>::kBytes;
   static constexpr uint32_t kRingOff = kCovOff + kSC * CovStage<CT>::kBytes;
-  static constexpr uint32_t kWarpBytes = kRingOff + kRingBytes1;
-  static constexpr uint32_t kRecOff = kP * kWarpBytes;
+  static constexpr uint32_t kRecOff = kRingOff + kP * kRingBytes1;
   static constexpr uint32_t kTotal = kRecOff + kC * 2u * kRecBufBytes;
-  static_assert(kWarpBytes % 128u == 0u, "stage alignment");
+  static_assert(kCovOff % 128u == 0u && kRingOff % 128u == 0u, "stage alignment");
 };
 
 struct Shared {
@@ -148,8 +167,10 @@ struct Shared {
   uint32_t flush[kP];  // forced batch boundary (a tail value): the accumulate warp may take the short batch [head, flush)
   uint32_t tile_end[kP][kSC];  // tail after the tile that last used covariance stage s
   double probe_pose[kP][12];   // per probe warp: R (9, row-major) | t (3) of the factor run it is working on (multi-factor launches)
-  alignas(8) uint64_t bar_x[kP][kSX];
-  alignas(8) uint64_t bar_c[kP][kSC];
+  alignas(8) uint64_t full_x[kSX];   // coordinate stage s has landed (1 arrival + tx bytes)
+  alignas(8) uint64_t empty_x[kSX];  // every probe warp is done reading it (kP arrivals)
+  alignas(8) uint64_t full_c[kSC];   // covariance stage s has landed
+  alignas(8) uint64_t empty_c[kSC];  // every probe warp's accumulate warp has consumed the tile's hits (kP arrivals)
 };
 
 // tiles of CTA c: [c * T / G, (c + 1) * T / G) -- contiguous and balanced; the host uses the same formula for the slots
@@ -276,10 +297,18 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     sh.flush[tid] = 0u;
 #pragma unroll
     for (int s = 0; s < kSC; s++) sh.tile_end[tid][s] = 0u;
+  }
+  if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kSX; s++) mbar_init(&sh.bar_x[tid][s], 1u);
+    for (int s = 0; s < kSX; s++) {
+      mbar_init(&sh.full_x[s], 1u);
+      mbar_init(&sh.empty_x[s], kP);
+    }
 #pragma unroll
-    for (int s = 0; s < kSC; s++) mbar_init(&sh.bar_c[tid][s], 1u);
+    for (int s = 0; s < kSC; s++) {
+      mbar_init(&sh.full_c[s], 1u);
+      mbar_init(&sh.empty_c[s], kP);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -288,26 +317,90 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
   const uint32_t tile_lo = cta_tile_begin(blockIdx.x, num_tiles, G);
   const uint32_t tile_hi = cta_tile_begin(blockIdx.x + 1, num_tiles, G);
 
+  if (warp >= kP + kC) {
+    // ================================================ PRODUCER warps ================================================
+    // aux warp 0 streams the coordinate planes (+ frozen correspondences), aux warp 1 the covariance planes: one lane each,
+    // running ahead of the probe warps as far as the stages allow -- across factor boundaries, too.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_AUX));
+    const int role = warp - (kP + kC);
+    if (role > 1 || lane != 0) return;
+    uint32_t j = 0u;  // CTA tiles issued so far: stage = j % S, use count = j / S
+    uint32_t tile = tile_lo;
+#ifdef B2_V2_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
+    while (tile < tile_hi) {
+      const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
+      const uint32_t n_pad = dg->n_pad;
+      const uint32_t f_tile_begin = dg->tile_begin, f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
+      const uint32_t run_end = min(tile_hi, f_tile_begin + f_num_tiles);
+      const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
+      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
+      const int32_t* __restrict__ corr = dg->corr;
+      uint32_t pt = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles);
+      for (; tile < run_end; tile++, j++) {
+        const uint32_t base = pt * kTile;
+        const uint32_t cnt = base >= n_pad ? 0u : min(static_cast<uint32_t>(kTile), n_pad - base);  // multiple of 32
+        if (role == 0) {
+          const uint32_t s = j % kSX;
+          B2_T0(tw);
+          if (j >= static_cast<uint32_t>(kSX)) mbar_wait(&sh.empty_x[s], ((j / kSX) - 1u) & 1u);
+          B2_TACC(0, tw);
+          fence_proxy_async();  // the stage was read through the generic proxy
+          const uint32_t dst = smem_u32(dyn_smem + L::kXyzOff + s * XS::kBytes);
+          mbar_expect_tx(&sh.full_x[s], cnt * (3u * static_cast<uint32_t>(sizeof(PT)) + (MODE == MODE_ERROR ? 4u : 0u)));
+          if (cnt) {
+            const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(PT));
+#pragma unroll
+            for (int a = 0; a < 3; a++) bulk_g2s(dst + a * XS::kPlane, px + static_cast<size_t>(a) * n_pad + base, bytes, &sh.full_x[s]);
+            if (MODE == MODE_ERROR) bulk_g2s(dst + XS::kCorrOff, corr + base, cnt * 4u, &sh.full_x[s]);
+          }
+        } else {
+          const uint32_t s = j % kSC;
+          B2_T0(tw);
+          if (j >= static_cast<uint32_t>(kSC)) mbar_wait(&sh.empty_c[s], ((j / kSC) - 1u) & 1u);
+          B2_TACC(0, tw);
+          fence_proxy_async();
+          const uint32_t dst = smem_u32(dyn_smem + L::kCovOff + s * CS::kBytes);
+          mbar_expect_tx(&sh.full_c[s], cnt * 6u * static_cast<uint32_t>(sizeof(CT)));
+          if (cnt) {
+            const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(CT));
+#pragma unroll
+            for (int a = 0; a < 6; a++) bulk_g2s(dst + a * CS::kPlane, cv + static_cast<size_t>(a) * n_pad + base, bytes, &sh.full_c[s]);
+          }
+        }
+        pt += perm_stride;
+        if (pt >= f_num_tiles) pt -= f_num_tiles;
+      }
+    }
+#ifdef B2_V2_TIMING
+    tacc[7] = clock64() - t_begin;
+    for (int k = 0; k < 8; k++) g_warp_cycles[(blockIdx.x * 32 + warp) * 8 + k] = tacc[k];
+#endif
+    return;
+  }
+
   if (warp < kP) {
     // ================================================= PROBE warps =================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_PRODUCER));
     const int p = warp;
-    unsigned char* const wbase = dyn_smem + static_cast<size_t>(p) * L::kWarpBytes;
-    const uint32_t xyz_s = smem_u32(wbase + L::kXyzOff), cov_s = smem_u32(wbase + L::kCovOff);
-    double2* const ring = reinterpret_cast<double2*>(wbase + L::kRingOff);
+    double2* const ring = reinterpret_cast<double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
     uint32_t tail = 0u, run = 0u;
-    uint32_t nx = 0u, nc = 0u;  // warp tiles whose coordinate / covariance stage has been consumed so far (all runs): stage = n % S, parity = (n / S) & 1
+    uint32_t j = 0u;    // CTA tiles this warp has processed so far (all runs): stage = j % S, use count = j / S
+    uint32_t rel = 0u;  // CTA tiles whose covariance stage this warp has released
     uint32_t head_seen = 0u;
     uint32_t tile = tile_lo;
+#ifdef B2_V2_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
     while (tile < tile_hi) {
       const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
       const uint32_t n = dg->n;
-      const uint32_t n_pad = dg->n_pad;
       const uint32_t f_tile_begin = dg->tile_begin;
       const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
       const uint32_t out_index = dg->out_index;
-      const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
-      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
       const double* __restrict__ records = dg->records;
       int32_t* __restrict__ corr = dg->corr;
       const VoxelBucket* __restrict__ buckets = dg->buckets;
@@ -330,95 +423,50 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       // Virtual tile v of the factor (the CTA owns a contiguous range of them) is physical tile (v * S) mod n_tiles with
       // S ~ 0.618 n_tiles coprime to n_tiles: every CTA samples the (Morton-ordered) cloud quasi-uniformly.
       const uint32_t f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
-      auto phys_tile = [&](uint32_t vt) { return static_cast<uint32_t>(static_cast<unsigned long long>(vt - f_tile_begin) * perm_stride % f_num_tiles); };
-      auto next_tile = [&](uint32_t pt) {
-        pt += perm_stride;
-        return pt >= f_num_tiles ? pt - f_num_tiles : pt;
-      };
-      // elements of the warp tile that exist in the padded planes (multiple of 32; 0 beyond the cloud)
-      auto tile_count = [&](uint32_t base) -> uint32_t { return base >= n_pad ? 0u : min(static_cast<uint32_t>(kWarpPoints), n_pad - base); };
-      // ---- bulk-copy issue (lane 0 only) ----
-      auto issue_xyz = [&](uint32_t pt, uint32_t k) {  // k: running stage counter of the tile
-        const uint32_t s = k % kSX;
-        const uint32_t base = pt * kTile + p * kWarpPoints, cnt = tile_count(base);
-        uint64_t* bar = &sh.bar_x[p][s];
-        const uint32_t dst = xyz_s + s * XS::kBytes;
-        mbar_expect_tx(bar, cnt * (3u * static_cast<uint32_t>(sizeof(PT)) + (MODE == MODE_ERROR ? 4u : 0u)));
-        if (cnt) {
-          const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(PT));
-#pragma unroll
-          for (int a = 0; a < 3; a++) bulk_g2s(dst + a * XS::kPlane, px + static_cast<size_t>(a) * n_pad + base, bytes, bar);
-          if (MODE == MODE_ERROR) bulk_g2s(dst + XS::kCorrOff, corr + base, cnt * 4u, bar);
-        }
-      };
-      auto issue_cov = [&](uint32_t pt, uint32_t k) {
-        const uint32_t s = k % kSC;
-        const uint32_t base = pt * kTile + p * kWarpPoints, cnt = tile_count(base);
-        uint64_t* bar = &sh.bar_c[p][s];
-        const uint32_t dst = cov_s + s * CS::kBytes;
-        mbar_expect_tx(bar, cnt * 6u * static_cast<uint32_t>(sizeof(CT)));
-        if (cnt) {
-          const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(CT));
-#pragma unroll
-          for (int a = 0; a < 6; a++) bulk_g2s(dst + a * CS::kPlane, cv + static_cast<size_t>(a) * n_pad + base, bytes, bar);
-        }
-      };
+      uint32_t pt_cur = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles);
+      uint32_t grid_base = tail;  // the accumulate warp's batches of this run start at grid_base + 32 i (until a forced boundary)
 
-      const uint32_t K = run_end - tile;  // warp tiles of this run
-      uint32_t grid_base = tail;          // the accumulate warp's batches of this run start at grid_base + 32 i (until a forced boundary)
-      // prologue: every stage is free (the previous run was drained and acknowledged)
-      uint32_t pt_x = phys_tile(tile), pt_c = pt_x, pt_cur = pt_x;
-      if (lane == 0) fence_proxy_async();
-      for (uint32_t k = 0; k < static_cast<uint32_t>(kSX - 1) && k < K; k++) {
-        if (lane == 0) issue_xyz(pt_x, nx + k);
-        pt_x = next_tile(pt_x);
-      }
-      for (uint32_t k = 0; k < static_cast<uint32_t>(kLC) && k < K; k++) {
-        if (lane == 0) issue_cov(pt_c, nc + k);
-        pt_c = next_tile(pt_c);
-      }
+      // this warp's share of covariance stage (r % kSC) goes back to the producer once the accumulate warp has consumed the
+      // last hit of tile r (`head` >= tile_end); forces a batch boundary if the accumulate warp could not get there otherwise
+      auto release_tile = [&](uint32_t r) {
+        const uint32_t s = r % kSC;
+        const uint32_t e = sh.tile_end[p][s];
+        if (static_cast<int32_t>(head_seen - e) < 0) {
+          head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
+          if (static_cast<int32_t>(head_seen - e) < 0) {
+            // can the accumulate warp get there with full batches?  (deterministic: depends on hit counts only)
+            const uint32_t need = grid_base + ((e - grid_base + 31u) & ~31u);
+            if (static_cast<int32_t>(tail - need) < 0) {
+              if (lane == 0) st_release(&sh.flush[p], tail);  // forced batch boundary at the current tail
+              grid_base = tail;
+            }
+            Backoff bo(32u, 256u);
+            do {
+              bo.wait();
+              head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
+            } while (static_cast<int32_t>(head_seen - e) < 0);
+          }
+        }
+        if (lane == 0) mbar_arrive(&sh.empty_c[s]);
+      };
 
 #pragma unroll 1
-      for (uint32_t k = 0; k < K; k++, pt_cur = next_tile(pt_cur)) {
-        // ---- lookahead issues ----
-        if (k + kSX - 1 < K) {  // the stage of tile k - 1: this warp finished reading it (the ballot below synchronised the lanes)
-          if (lane == 0) {
-            fence_proxy_async();
-            issue_xyz(pt_x, nx + kSX - 1);
-          }
-          pt_x = next_tile(pt_x);
-        }
-        if (k + kLC < K) {
-          // covariance stage of tile k + kLC - kSC: free once the accumulate warp has consumed that tile's last hit
-          const uint32_t s = (nc + kLC) % kSC;
-          const uint32_t e = sh.tile_end[p][s];
-          if (static_cast<int32_t>(head_seen - e) < 0) {
-            head_seen = ld_acquire(&sh.head[p]);
-            if (static_cast<int32_t>(head_seen - e) < 0) {
-              // can the accumulate warp get there with full batches?  (deterministic: depends on hit counts only)
-              const uint32_t need = grid_base + ((e - grid_base + 31u) & ~31u);
-              if (static_cast<int32_t>(tail - need) < 0) {
-                if (lane == 0) st_release(&sh.flush[p], tail);  // forced batch boundary at the current tail
-                grid_base = tail;
-              }
-              Backoff bo(32u, 256u);
-              do {
-                bo.wait();
-                head_seen = ld_acquire(&sh.head[p]);
-              } while (static_cast<int32_t>(head_seen - e) < 0);
-            }
-          }
-          if (lane == 0) {
-            fence_proxy_async();
-            issue_cov(pt_c, nc + kLC);
-          }
-          pt_c = next_tile(pt_c);
+      for (; tile < run_end; tile++, j++) {
+        {
+          B2_T0(tw);
+          if (j - rel >= static_cast<uint32_t>(kRet)) release_tile(rel++);
+          B2_TACC(0, tw);
         }
 
         // ---- this tile's coordinates ----
-        const uint32_t sx = nx % kSX;
-        mbar_wait(&sh.bar_x[p][sx], (nx / kSX) & 1u);
-        const unsigned char* xs = wbase + L::kXyzOff + sx * XS::kBytes;
+        const uint32_t sx = j % kSX;
+        {
+          B2_T0(tw);
+          mbar_wait(&sh.full_x[sx], (j / kSX) & 1u);
+          B2_TACC(1, tw);
+        }
+        B2_T0(t_work);
+        const unsigned char* xs = dyn_smem + L::kXyzOff + sx * XS::kBytes;
         const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
         double u[kPPL][3];
         int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
@@ -427,7 +475,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         BucketGroup grp[kPPL];
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
-          const int li = lane + 32 * q;
+          const int li = p * kWarpPoints + lane + 32 * q;
           ok[q] = base + 32 * q < n;
           const double x = static_cast<double>(reinterpret_cast<const PT*>(xs)[li]);
           const double y = static_cast<double>(reinterpret_cast<const PT*>(xs + XS::kPlane)[li]);
@@ -448,6 +496,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 #endif
           }
         }
+        // every lane has read its coordinates: the stage goes back to the producer (one arrival per probe warp)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_x[sx]);
         uint32_t mask[kPPL], cnt = 0u;
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
@@ -469,20 +520,21 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             }
             if (ok[q]) corr[base + 32 * q] = id[q];
           }
-          mask[q] = __ballot_sync(0xffffffffu, ok[q] && id[q] >= 0);  // also: every lane is done with the coordinate stage
+          mask[q] = __ballot_sync(0xffffffffu, ok[q] && id[q] >= 0);
           cnt += __popc(mask[q]);
         }
-        nx++;
-        const uint32_t sc = nc % kSC;
+        const uint32_t sc = j % kSC;
+        B2_TACC(2, t_work);
+        B2_T0(t_ring);
         if (cnt != 0u) {
           // room in the ring
           if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
-            head_seen = ld_acquire(&sh.head[p]);
+            head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
             if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
               Backoff bo(32u, 256u);
               do {
                 bo.wait();
-                head_seen = ld_acquire(&sh.head[p]);
+                head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
               } while (tail + cnt - head_seen > static_cast<uint32_t>(kRing));
             }
           }
@@ -490,7 +542,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           for (int q = 0; q < kPPL; q++) {
             if ((mask[q] >> lane) & 1u) {
               const uint32_t slot = (tail + __popc(mask[q] & ((1u << lane) - 1u))) & (kRing - 1);
-              const uint32_t loc = sc * kWarpPoints + lane + 32 * q;  // where the accumulate warp finds this point's covariance
+              const uint32_t loc = sc * kTile + p * kWarpPoints + lane + 32 * q;  // where the accumulate warp finds this point's covariance
               const unsigned long long bits = static_cast<unsigned long long>(loc) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
               ring[slot] = make_double2(u[q][0], u[q][1]);
               ring[kRing + slot] = make_double2(u[q][2], __longlong_as_double(static_cast<long long>(bits)));
@@ -503,38 +555,61 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             tail += __popc(mask[q]);
           }
         }
+        B2_TACC(3, t_ring);
         // the tile's covariances must have landed before its hits become visible to the accumulate warp
-        mbar_wait(&sh.bar_c[p][sc], (nc / kSC) & 1u);
-        nc++;
+        {
+          B2_T0(tw);
+          mbar_wait(&sh.full_c[sc], (j / kSC) & 1u);
+          B2_TACC(4, tw);
+        }
         __syncwarp();
         if (lane == 0) {
           sh.tile_end[p][sc] = tail;
           st_release(&sh.tail[p], tail);
         }
+        pt_cur += perm_stride;
+        if (pt_cur >= f_num_tiles) pt_cur -= f_num_tiles;
       }
       // end of this CTA's run of the factor: publish, then wait until the accumulate warp has drained the ring
       run++;
       __syncwarp();
       if (lane == 0) st_release(&sh.done[p], run);
       {
+        B2_T0(tw);
         Backoff bo(128u, 512u);
         while (ld_acquire(&sh.ack[p]) != run) bo.wait();
+        B2_TACC(5, tw);
       }
       head_seen = tail;
-      tile = run_end;
+      __syncwarp();
+      // everything published so far has been consumed: hand the outstanding covariance stages back
+      while (rel < j) {
+        if (lane == 0) mbar_arrive(&sh.empty_c[rel % kSC]);
+        rel++;
+      }
     }
+#ifdef B2_V2_TIMING
+    tacc[7] = clock64() - t_begin;
+    if (lane == 0)
+      for (int k = 0; k < 8; k++) g_warp_cycles[(blockIdx.x * 32 + warp) * 8 + k] = tacc[k];
+#endif
   } else {
     // =============================================== ACCUMULATE warps ===============================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_CONSUMER));
     const int cw = warp - kP;        // accumulate warp index
     const int ctid = tid - kP * 32;  // thread index within the accumulate group
     unsigned char* const recbuf = dyn_smem + L::kRecOff + static_cast<size_t>(cw) * 2u * kRecBufBytes;
+    const unsigned char* const cov_stages = dyn_smem + L::kCovOff;
     uint32_t head[kRingsPerConsumer];  // items taken (fetched) from each of this warp's rings
 #pragma unroll
     for (int r = 0; r < kRingsPerConsumer; r++) head[r] = 0u;
     uint32_t run = 0u;
     uint32_t tile = tile_lo;
     double acc[kAcc];
+#ifdef B2_V2_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
     while (tile < tile_hi) {
       const uint32_t f = SINGLE ? 0u : __ldg(tile_factor + tile);
       consumer_barrier();  // previous flush is done with sh.desc
@@ -625,7 +700,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         if (fin) finished |= 1u << r;
         // request the target records of the batch: 5 x 16 B per hit, straight into shared memory (no registers, no scoreboard)
         if (static_cast<uint32_t>(lane) < nb) {
-          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + static_cast<size_t>(p) * L::kWarpBytes + L::kRingOff);
+          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
           const uint32_t slot = (hd + lane) & (kRing - 1);
           const int id = static_cast<int>(static_cast<unsigned long long>(__double_as_longlong(rg[kRing + slot].y)) >> 32);
           const char* src = reinterpret_cast<const char*>(records + static_cast<size_t>(id) * kRecordDoubles);
@@ -650,8 +725,13 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         if (!cur.valid) {
           const int r = next_ring(rot);
           if (r < 0) break;
+          B2_T0(tw);
           fetch(r, true, cur, buf);
+          B2_TACC(0, tw);
           rot = (r + 1) % kRingsPerConsumer;
+#ifdef B2_V2_TIMING
+          tacc[4]++;
+#endif
         }
         // try to get the following batch on its way before computing this one
         nxt.valid = false;
@@ -659,15 +739,20 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           const int r = next_ring(rot);
           if (r >= 0 && fetch(r, false, nxt, buf ^ 1u)) rot = (r + 1) % kRingsPerConsumer;
         }
+        B2_T0(t_cp);
         if (nxt.valid)
           cp_async_wait<1>();
         else
           cp_async_wait<0>();
+        B2_TACC(1, t_cp);
+        B2_T0(t_comp);
+#ifdef B2_V2_TIMING
+        tacc[5]++;
+#endif
         // ---- compute `cur` from shared memory only ----
         {
           const int p = cw + cur.r * kC;
-          const unsigned char* wb = dyn_smem + static_cast<size_t>(p) * L::kWarpBytes;
-          const double2* rg = reinterpret_cast<const double2*>(wb + L::kRingOff);
+          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
           const bool valid = static_cast<uint32_t>(lane) < cur.nb;
           const uint32_t slot = (cur.hd + lane) & (kRing - 1);
           const double2 q0 = rg[slot], q1 = rg[kRing + slot];
@@ -681,15 +766,15 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             T.r45 = rr[2];
             T.r67 = rr[3];
             T.r89 = rr[4];
-            const uint32_t cs = loc / kWarpPoints, li = loc % kWarpPoints;
-            const CT* cp = reinterpret_cast<const CT*>(wb + L::kCovOff + cs * CS::kBytes) + li;
+            const uint32_t cs = loc / kTile, li = loc % kTile;
+            const CT* cp = reinterpret_cast<const CT*>(cov_stages + cs * CS::kBytes) + li;
             SourceCov A;
             A.a00 = static_cast<double>(cp[0]);
-            A.a01 = static_cast<double>(cp[kWarpPoints]);
-            A.a02 = static_cast<double>(cp[2 * kWarpPoints]);
-            A.a11 = static_cast<double>(cp[3 * kWarpPoints]);
-            A.a12 = static_cast<double>(cp[4 * kWarpPoints]);
-            A.a22 = static_cast<double>(cp[5 * kWarpPoints]);
+            A.a01 = static_cast<double>(cp[kTile]);
+            A.a02 = static_cast<double>(cp[2 * kTile]);
+            A.a11 = static_cast<double>(cp[3 * kTile]);
+            A.a12 = static_cast<double>(cp[4 * kTile]);
+            A.a22 = static_cast<double>(cp[5 * kTile]);
             accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
           }
 #else
@@ -702,12 +787,20 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             if (cur.fin) st_release(&sh.ack[p], run);
           }
         }
+        B2_TACC(2, t_comp);
         cur = nxt;
         buf ^= 1u;
       }
+      B2_T0(t_fl);
       flush_factor<MODE>(sh, acc, ctid, partials, counters, out, pe, sig);
+      B2_TACC(3, t_fl);
       tile = run_end;
     }
+#ifdef B2_V2_TIMING
+    tacc[7] = clock64() - t_begin;
+    if (lane == 0)
+      for (int k = 0; k < 8; k++) g_warp_cycles[(blockIdx.x * 32 + warp) * 8 + k] = tacc[k];
+#endif
   }
 }
 

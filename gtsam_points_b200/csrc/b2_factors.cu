@@ -385,7 +385,7 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_V2_REGS_PRODUCER 88
 #endif
 #ifndef B2_V2_REGS_CONSUMER
-#define B2_V2_REGS_CONSUMER 168
+#define B2_V2_REGS_CONSUMER 136
 #endif
 #ifndef B2_V2_RING
 #define B2_V2_RING 128
@@ -399,8 +399,11 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #ifndef B2_V2_COV_STAGES
 #define B2_V2_COV_STAGES 4
 #endif
-#ifndef B2_V2_COV_AHEAD
-#define B2_V2_COV_AHEAD 1
+#ifndef B2_V2_COV_RETAIN
+#define B2_V2_COV_RETAIN 2
+#endif
+#ifndef B2_V2_REGS_AUX
+#define B2_V2_REGS_AUX 24
 #endif
 #ifndef B2_V2_PREFETCH_RECORDS
 #define B2_V2_PREFETCH_RECORDS 1  // probe warps start the voxel record lines of every hit towards L2
@@ -503,6 +506,8 @@ struct Group {
   int kind, pb, cb;
   std::vector<size_t> members;  // indices into the set's factor list
   std::vector<uint64_t> gen;    // per member: the factor's params_gen its device descriptor was built from
+  std::vector<uint64_t> vm_gen; // per member: generation of its voxel map (device pointers / ids change on insert())
+  std::vector<FactorDesc> h_descs;  // host copy of the device descriptors (patched and re-uploaded when a generation moves)
   FactorDesc* d_descs = nullptr;
   uint32_t* d_tile_factor = nullptr;
   uint32_t num_tiles = 0;
@@ -586,13 +591,24 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
   const bool single = h_pose != nullptr && s->factors.size() == 1 && s->groups.size() == 1 && s->groups[0].fn_single[mode] != nullptr;
   if (single) std::memcpy(pa.m, h_pose, sizeof(pa.m));
   for (auto& g : s->groups) {
-    // tuning setters called after the set was built (set_max_correspondence_distance): refresh the device descriptors,
-    // stream-ordered before the launch -- like the reference, the new value takes effect at the next correspondence update
+    // tuning setters called after the set was built (set_max_correspondence_distance) and voxel maps that grew since
+    // (b2_voxelmap_insert): refresh the device descriptors, stream-ordered before the launch -- like the reference, a new
+    // value takes effect at the next correspondence update
     for (size_t k = 0; k < g.members.size(); k++) {
       const b2_factor* f = s->factors[g.members[k]];
-      if (f->params_gen != g.gen[k]) {
-        B2_CUDA(cudaMemcpyAsync(&g.d_descs[k].max_sq, &f->max_corr_sq, sizeof(double), cudaMemcpyHostToDevice, st));
+      const uint64_t vgen = f->voxelmap ? f->voxelmap->generation : 0;
+      if (f->params_gen != g.gen[k] || vgen != g.vm_gen[k]) {
+        FactorDesc& d = g.h_descs[k];
+        d.max_sq = f->max_corr_sq;
+        if (f->voxelmap) {
+          d.buckets = f->voxelmap->d_buckets;
+          d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets / kGroup - 1);
+          d.inv_leaf = f->voxelmap->inv_resolution;
+          d.records = f->voxelmap->d_records;
+        }
+        B2_CUDA(cudaMemcpyAsync(&g.d_descs[k], &d, sizeof(FactorDesc), cudaMemcpyHostToDevice, st));
         g.gen[k] = f->params_gen;
+        g.vm_gen[k] = vgen;
       }
     }
     (single ? g.fn_single[mode] : g.fn[mode])<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem[mode], st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials,
@@ -804,10 +820,12 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       d.perm_stride = golden_stride(d.num_tiles);
       d.out_index = static_cast<uint32_t>(g.members[k]);
       g.gen.push_back(f->params_gen);
+      g.vm_gen.push_back(f->voxelmap ? f->voxelmap->generation : 0);
       tile_cursor += d.num_tiles;
       tile_factor.insert(tile_factor.end(), d.num_tiles, static_cast<uint32_t>(k));
     }
     g.num_tiles = tile_cursor;
+    auto keep_host_copy = [&]() { g.h_descs = descs; };
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb, false);
       g.fn_single[mode] = (g.kind == B2_FACTOR_VGICP && F == 1) ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;
@@ -836,6 +854,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
         slot_cursor += d.num_slots[mode];
       }
     }
+    keep_host_copy();  // after the per-mode slot bookkeeping above has been written into `descs`
     cudaError_t e;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&g.d_descs), descs.size() * sizeof(FactorDesc))) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void**>(&g.d_tile_factor), tile_factor.size() * sizeof(uint32_t))) != cudaSuccess) {
@@ -1125,15 +1144,11 @@ b2_status b2_factor_set_error(b2_factor_set* s, const double* deltas_eval, doubl
   return B2_OK;
 }
 
-#ifdef B2_WS_TIMING
-// development aid (not part of the ABI): fetch and reset the per-CTA timestamps of the last launch
-__attribute__((visibility("default"))) int b2_debug_cta_times(unsigned long long* out, int n) {
+#ifdef B2_V2_TIMING
+// development aid (not part of the ABI): per-warp cycle totals of the last VGICP launch, [block][32 warps][8 slots]
+__attribute__((visibility("default"))) int b2_debug_warp_cycles(unsigned long long* out, int blocks) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, ws::g_cta_times, sizeof(unsigned long long) * n * 4);
-  std::vector<unsigned long long> init(1024 * 4, 0ull);
-  for (int i = 0; i < 1024; i++) init[i * 4 + 3] = ~0ull;
-  cudaMemcpyToSymbol(ws::g_cta_times, init.data(), sizeof(unsigned long long) * 1024 * 4);
-  return 0;
+  return static_cast<int>(cudaMemcpyFromSymbol(out, v2::g_warp_cycles, sizeof(unsigned long long) * blocks * 32 * 8));
 }
 #endif
 
@@ -1149,6 +1164,29 @@ b2_status b2_factor_linearize(b2_factor* f, const double* delta, b2_linearized* 
   B2_REQUIRE(f && delta && out, "b2_factor_linearize: NULL argument");
   B2_TRY(ensure_self_set(f));
   return b2_factor_set_linearize(f->self_set, delta, out);
+}
+
+b2_status b2_factor_issue_linearize(b2_factor* f, const double* delta, double* d_out) {
+  B2_REQUIRE(f && delta && d_out, "b2_factor_issue_linearize: NULL argument");
+  B2_TRY(ensure_self_set(f));
+  return b2_factor_set_issue_linearize(f->self_set, delta, d_out);
+}
+
+b2_status b2_factor_issue_error(b2_factor* f, const double* delta_eval, double* d_out_error) {
+  B2_REQUIRE(f && delta_eval && d_out_error, "b2_factor_issue_error: NULL argument");
+  B2_TRY(ensure_self_set(f));
+  if (!f->linearized) {  // integrated_vgicp_factor_impl.hpp:183-185: the first evaluation establishes the correspondences
+    b2_linearized tmp;
+    B2_TRY(b2_factor_set_linearize(f->self_set, delta_eval, &tmp));
+  }
+  return b2_factor_set_issue_error(f->self_set, delta_eval, d_out_error);
+}
+
+b2_status b2_factor_sync(b2_factor* f) {
+  B2_REQUIRE(f != nullptr, "b2_factor_sync: factor is NULL");
+  B2_CUDA(cudaSetDevice(f->ctx->device));
+  B2_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return B2_OK;
 }
 
 b2_status b2_factor_error(b2_factor* f, const double* delta_eval, double* out_error) {

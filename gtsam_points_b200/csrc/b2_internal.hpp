@@ -113,6 +113,11 @@ struct b2_voxelmap {
   double* d_records = nullptr;   // num_voxels x 10
   int32_t* d_coords = nullptr;   // num_voxels x 3 (id order), kept for download
   size_t device_bytes = 0;
+  // incremental insertion state (ann/incremental_voxelmap.hpp:13-28): LRU bookkeeping as in the CPU map
+  uint32_t* d_lru = nullptr;     // per voxel: lru_counter value of the last insert() that touched it
+  size_t capacity = 0;           // voxels the record / coord / lru arrays can hold
+  size_t lru_horizon = 10, lru_clear_cycle = 10, lru_counter = 0;
+  uint64_t generation = 0;       // bumped whenever the device pointers / voxel ids change: factor sets refresh their descriptors
 };
 
 struct b2_kdtree {

@@ -193,6 +193,153 @@ struct DevBuf {
   }
 };
 
+
+// ---- k nearest neighbours (k <= B2_KNN_MAX_K) and covariance estimation on top of it ------------------------------------
+constexpr int kKnnWarps = 4;  // warps per CTA of the k-NN kernels (scratch: k x 32 x 12 bytes per warp)
+
+// queries: device array nq x stride.  out_index / out_sq_dist: nq x k, sorted by distance, (-1, max_sq) beyond the number found.
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KdTreeView view, const double* __restrict__ q, int stride, size_t nq, int k, double max_sq,
+                                                             const uint32_t* __restrict__ leaf_index, long long* __restrict__ out_index, double* __restrict__ out_sq) {
+  extern __shared__ __align__(16) unsigned char knn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sdist = reinterpret_cast<double*>(knn_smem) + static_cast<size_t>(warp) * k * 32;
+  int* sidx = reinterpret_cast<int*>(reinterpret_cast<double*>(knn_smem) + static_cast<size_t>(kKnnWarps) * k * 32) + static_cast<size_t>(warp) * k * 32;
+  const size_t i = (blockIdx.x * static_cast<size_t>(kKnnWarps) + warp) * 32 + lane;
+  const bool active = i < nq;
+  const size_t ii = active ? i : 0;
+  kdtree_knn_warp(view, q[ii * stride], q[ii * stride + 1], q[ii * stride + 2], active, k, max_sq, sdist, sidx, lane);
+  if (!active) return;
+  for (int j = 0; j < k; j++) {
+    const int s = sidx[j * 32 + lane];
+    out_index[i * k + j] = s < 0 ? -1ll : static_cast<long long>(leaf_index[s]);
+    out_sq[i * k + j] = sdist[j * 32 + lane];
+  }
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (ascending eigenvalues, eigenvectors in the columns of V): the same
+// rotation sequence as the CPU oracle's restatement, robust for the rank-deficient covariances of planar neighbourhoods
+__device__ __forceinline__ void jacobi_eigen3(double A[3][3], double w[3], double V[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int q = p + 1; q < 3; q++) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  // ascending order (3-element sorting network on (w, column))
+  w[0] = A[0][0], w[1] = A[1][1], w[2] = A[2][2];
+  auto swap_cols = [&](int a, int b) {
+    if (w[b] < w[a]) {
+      const double tw = w[a];
+      w[a] = w[b];
+      w[b] = tw;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double tv = V[i][a];
+        V[i][a] = V[i][b];
+        V[i][b] = tv;
+      }
+    }
+  };
+  swap_cols(0, 1);
+  swap_cols(1, 2);
+  swap_cols(0, 1);
+}
+
+// estimate_covariances (src/gtsam_points/features/covariance_estimation.cpp:18-77) for the tree's own points: each lane owns
+// one point (leaf order: a warp's 32 queries are spatial neighbours, the packet walk is shared almost entirely), finds its
+// k nearest neighbours (itself included), sums p and p p^T over them in ascending-distance order, cov = (S_pp - mean S_p^T) / k,
+// then the EIG regularisation: eigenvalues replaced by `ev` (ascending-eigenvalue order), cov = V diag(ev) V^T.
+__global__ void __launch_bounds__(kKnnWarps * 32) covariance_kernel(KdTreeView view, size_t n, int k, double ev0, double ev1, double ev2,
+                                                                    const uint32_t* __restrict__ leaf_index, double* __restrict__ out_cov /* n x 9, caller order */) {
+  extern __shared__ __align__(16) unsigned char knn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sdist = reinterpret_cast<double*>(knn_smem) + static_cast<size_t>(warp) * k * 32;
+  int* sidx = reinterpret_cast<int*>(reinterpret_cast<double*>(knn_smem) + static_cast<size_t>(kKnnWarps) * k * 32) + static_cast<size_t>(warp) * k * 32;
+  const size_t i = (blockIdx.x * static_cast<size_t>(kKnnWarps) + warp) * 32 + lane;
+  const bool active = i < n;
+  auto point = [&](size_t j, double& x, double& y, double& z) {
+    if (view.f32) {
+      const float4 p = __ldg(static_cast<const float4*>(view.leaf_points) + j);
+      x = p.x, y = p.y, z = p.z;
+    } else {
+      const double2* pp = static_cast<const double2*>(view.leaf_points) + 2 * j;
+      const double2 a = __ldg(pp), b = __ldg(pp + 1);
+      x = a.x, y = a.y, z = b.x;
+    }
+  };
+  double qx = 0, qy = 0, qz = 0;
+  if (active) point(i, qx, qy, qz);
+  kdtree_knn_warp(view, qx, qy, qz, active, k, 1.7976931348623157e308, sdist, sidx, lane);
+  if (!active) return;
+  double* out = out_cov + static_cast<size_t>(leaf_index[i]) * 9;
+  if (sidx[(k - 1) * 32 + lane] < 0) {  // fewer than k neighbours: identity (covariance_estimation.cpp:27-31)
+#pragma unroll
+    for (int a = 0; a < 9; a++) out[a] = (a % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double sp[3] = {0, 0, 0}, sc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < k; j++) {
+    double p[3];
+    point(static_cast<size_t>(sidx[j * 32 + lane]), p[0], p[1], p[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      sp[a] = __dadd_rn(sp[a], p[a]);
+#pragma unroll
+      for (int b = 0; b < 3; b++) sc[a][b] = __dadd_rn(sc[a][b], __dmul_rn(p[a], p[b]));
+    }
+  }
+  const double kk = static_cast<double>(k);
+  double cov[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) cov[a][b] = __ddiv_rn(__dsub_rn(sc[a][b], __dmul_rn(__ddiv_rn(sp[a], kk), sp[b])), kk);
+  double w[3], V[3][3];
+  jacobi_eigen3(cov, w, V);
+  const double ev[3] = {ev0, ev1, ev2};
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) v += V[a][c] * ev[c] * V[b][c];
+      out[a * 3 + b] = v;
+    }
+}
+
+size_t knn_smem_bytes(int k) { return static_cast<size_t>(kKnnWarps) * k * 32 * (sizeof(double) + sizeof(int)); }
+
 }  // namespace
 }  // namespace b2
 
@@ -373,6 +520,70 @@ b2_status b2_kdtree_knn1(const b2_kdtree* t, const double* queries, int query_st
   if (out_sq_dist) B2_CUDA(cudaMemcpyAsync(out_sq_dist, ds.p, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
   return B2_OK;
+}
+
+b2_status b2_kdtree_knn(const b2_kdtree* t, const double* queries, int query_stride, size_t nq, int k, double max_sq_dist, int64_t* out_index, double* out_sq_dist) {
+  B2_REQUIRE(t != nullptr, "b2_kdtree_knn: tree is NULL");
+  B2_REQUIRE(nq == 0 || queries != nullptr, "b2_kdtree_knn: queries is NULL");
+  B2_REQUIRE(query_stride == 3 || query_stride == 4, "b2_kdtree_knn: query_stride must be 3 or 4");
+  B2_REQUIRE(k >= 1 && k <= B2_KNN_MAX_K, "b2_kdtree_knn: k must be in [1, %d] (got %d)", B2_KNN_MAX_K, k);
+  B2_REQUIRE(max_sq_dist >= 0.0, "b2_kdtree_knn: max_sq_dist must be >= 0");
+  if (nq == 0) return B2_OK;
+  if (k == 1) return b2_kdtree_knn1(t, queries, query_stride, nq, max_sq_dist, out_index, out_sq_dist);
+  B2_CUDA(cudaSetDevice(t->ctx->device));
+  cudaStream_t st = t->ctx->stream;
+  DevBuf dq, di, ds;
+  B2_CUDA(cudaMalloc(&dq.p, nq * query_stride * sizeof(double)));
+  B2_CUDA(cudaMalloc(&di.p, nq * k * sizeof(long long)));
+  B2_CUDA(cudaMalloc(&ds.p, nq * k * sizeof(double)));
+  B2_CUDA(cudaMemcpyAsync(dq.p, queries, nq * query_stride * sizeof(double), cudaMemcpyHostToDevice, st));
+  KdTreeView view{t->d_nodes, t->d_leaf_points, t->leaf_f32 ? 1 : 0};
+  const size_t smem = knn_smem_bytes(k);
+  B2_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(knn_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (t->n == 0) {
+    std::vector<long long> idx(nq * k, -1);
+    std::vector<double> sq(nq * k, max_sq_dist);
+    if (out_index) std::memcpy(out_index, idx.data(), idx.size() * sizeof(long long));
+    if (out_sq_dist) std::memcpy(out_sq_dist, sq.data(), sq.size() * sizeof(double));
+    return B2_OK;
+  }
+  knn_kernel<<<static_cast<unsigned>((nq + kKnnWarps * 32 - 1) / (kKnnWarps * 32)), kKnnWarps * 32, smem, st>>>(view, static_cast<const double*>(dq.p), query_stride, nq, k, max_sq_dist,
+                                                                                                             t->d_leaf_index, static_cast<long long*>(di.p), static_cast<double*>(ds.p));
+  B2_CUDA(cudaGetLastError());
+  if (out_index) B2_CUDA(cudaMemcpyAsync(out_index, di.p, nq * k * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (out_sq_dist) B2_CUDA(cudaMemcpyAsync(out_sq_dist, ds.p, nq * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
+b2_status b2_kdtree_estimate_covariances(const b2_kdtree* t, int k_neighbors, const double* eigen_values, double* out_cov3x3) {
+  B2_REQUIRE(t && out_cov3x3, "b2_kdtree_estimate_covariances: NULL argument");
+  B2_REQUIRE(k_neighbors >= 1 && k_neighbors <= B2_KNN_MAX_K, "b2_kdtree_estimate_covariances: k_neighbors must be in [1, %d]", B2_KNN_MAX_K);
+  const size_t n = t->n;
+  if (n == 0) return B2_OK;
+  B2_CUDA(cudaSetDevice(t->ctx->device));
+  cudaStream_t st = t->ctx->stream;
+  const double ev[3] = {eigen_values ? eigen_values[0] : 1e-3, eigen_values ? eigen_values[1] : 1.0, eigen_values ? eigen_values[2] : 1.0};  // covariance_estimation.hpp:19
+  DevBuf dc;
+  B2_CUDA(cudaMalloc(&dc.p, n * 9 * sizeof(double)));
+  KdTreeView view{t->d_nodes, t->d_leaf_points, t->leaf_f32 ? 1 : 0};
+  const size_t smem = knn_smem_bytes(k_neighbors);
+  B2_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(covariance_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  covariance_kernel<<<static_cast<unsigned>((n + kKnnWarps * 32 - 1) / (kKnnWarps * 32)), kKnnWarps * 32, smem, st>>>(view, n, k_neighbors, ev[0], ev[1], ev[2], t->d_leaf_index,
+                                                                                                                 static_cast<double*>(dc.p));
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaMemcpyAsync(out_cov3x3, dc.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
+b2_status b2_estimate_covariances(b2_ctx* ctx, const double* points, int point_stride, size_t n, int k_neighbors, const double* eigen_values, double* out_cov3x3) {
+  B2_REQUIRE(ctx && (n == 0 || (points && out_cov3x3)), "b2_estimate_covariances: NULL argument");
+  b2_kdtree* tree = nullptr;
+  B2_TRY(b2_kdtree_create(ctx, points, point_stride, n, &tree));  // covariance_estimation.cpp:19
+  const b2_status s = b2_kdtree_estimate_covariances(tree, k_neighbors, eigen_values, out_cov3x3);
+  b2_kdtree_destroy(tree);
+  return s;
 }
 
 }  // extern "C"

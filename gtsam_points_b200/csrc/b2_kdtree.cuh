@@ -47,7 +47,7 @@ __device__ __forceinline__ KdNodeGPU load_node(const KdNodeGPU* p) {
 // prefer, and lets every lane evaluate every point of a visited leaf.  All loads are warp-uniform (one L1 lookup,
 // broadcast), control flow is uniform, and the answer is unchanged: each lane prunes with its own lower bound
 // bound = max over the splits on the path that separate the lane's query from the subtree of (q_axis - thresh)^2, a node is
-// skipped only if best <= bound holds for every lane, and distances use the same operation order as kdtree_nn1.
+// skipped only if best <= bound holds for every lane, and distances use the CPU path's operation order.
 // Must be called by all 32 lanes; lanes with active == false take part in the votes but never need anything.
 __device__ __forceinline__ int kdtree_nn1_warp(const KdTreeView& t, double qx, double qy, double qz, bool active, double max_sq, double* out_sq) {
   constexpr unsigned kFull = 0xffffffffu;
@@ -110,61 +110,77 @@ __device__ __forceinline__ int kdtree_nn1_warp(const KdTreeView& t, double qx, d
   return active ? best_j : -1;
 }
 
-// Returns the leaf-order position of the nearest point with squared distance < max_sq (else -1); *out_sq = that distance.
-// Squared distance is evaluated as (dx*dx + dy*dy) + dz*dz with individually rounded operations, the same order as the
-// CPU oracle, so distances (and therefore arg-min decisions) are bit-identical to the float64 CPU path.
-__device__ __forceinline__ int kdtree_nn1(const KdTreeView& t, double qx, double qy, double qz, double max_sq, double* out_sq) {
+// k nearest neighbours, packet form: like kdtree_nn1_warp, each lane additionally keeps its k best candidates, sorted by
+// distance, in a warp-private scratch area laid out [slot][lane] (sdist: k x 32 doubles, sidx: k x 32 ints -- shared memory,
+// conflict-free).  KnnResult semantics (include/gtsam_points/ann/knn_result.hpp:44-109): slots start at (max_sq, -1); a
+// candidate enters iff its distance is strictly below the current worst (slot k - 1) and is placed after every stored
+// candidate whose distance is <= its own; a node is skipped only when no lane's worst exceeds its lower bound.  Exact.
+__device__ __forceinline__ void kdtree_knn_warp(const KdTreeView& t, double qx, double qy, double qz, bool active, int k, double max_sq, double* __restrict__ sdist,
+                                                int* __restrict__ sidx, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  for (int j = 0; j < k; j++) {
+    sdist[j * 32 + lane] = max_sq;
+    sidx[j * 32 + lane] = -1;
+  }
   uint32_t stack_node[kKdStackDepth];
-  double stack_cut[kKdStackDepth];
+  double stack_bound[kKdStackDepth];
   int sp = 0;
-  double best = max_sq;
-  int best_j = -1;
+  double worst = active ? max_sq : 0.0;
   uint32_t node_idx = 0;
-  double cut = -1.0;  // root is always visited
+  double bound = 0.0;
+  auto offer = [&](double d, int j) {
+    if (d < worst) {
+      int pos = k - 1;
+      while (pos > 0 && d < sdist[(pos - 1) * 32 + lane]) {
+        sdist[pos * 32 + lane] = sdist[(pos - 1) * 32 + lane];
+        sidx[pos * 32 + lane] = sidx[(pos - 1) * 32 + lane];
+        pos--;
+      }
+      sdist[pos * 32 + lane] = d;
+      sidx[pos * 32 + lane] = j;
+      worst = sdist[(k - 1) * 32 + lane];
+    }
+  };
   while (true) {
-    if (best > cut) {
-      // descend to a leaf, pushing far children
-      KdNodeGPU n = load_node(t.nodes + node_idx);
-      while (n.b < 4u) {
+    if (__any_sync(kFull, worst > bound)) {
+      const KdNodeGPU n = load_node(t.nodes + node_idx);  // warp-uniform address
+      if (n.b < 4u) {
         const double qa = n.b == 0u ? qx : (n.b == 1u ? qy : qz);
         const double diff = __dsub_rn(qa, n.thresh);
-        const uint32_t near_c = diff < 0.0 ? n.a : n.a + 1u;
-        const uint32_t far_c = diff < 0.0 ? n.a + 1u : n.a;
-        stack_node[sp] = far_c;
-        stack_cut[sp] = __dmul_rn(diff, diff);
+        const double d2 = __dmul_rn(diff, diff);
+        const bool left = diff < 0.0;
+        const bool need = worst > bound;
+        const int nl = __popc(__ballot_sync(kFull, need && left)), nr = __popc(__ballot_sync(kFull, need && !left));
+        const bool go_left = nl >= nr;
+        const bool mine = (left == go_left);
+        const double sep = bound > d2 ? bound : d2;
+        stack_node[sp] = go_left ? n.a + 1u : n.a;
+        stack_bound[sp] = mine ? sep : bound;
         sp++;
-        n = load_node(t.nodes + near_c);
+        node_idx = go_left ? n.a : n.a + 1u;
+        bound = mine ? bound : sep;
+        continue;
       }
       const uint32_t first = n.a, cnt = n.b - 4u;
       if (t.f32) {
         const float4* __restrict__ pts = static_cast<const float4*>(t.leaf_points);
         for (uint32_t j = first; j < first + cnt; j++) {
           const float4 p = __ldg(pts + j);
-          const double d = kd_sq_dist(static_cast<double>(p.x), static_cast<double>(p.y), static_cast<double>(p.z), qx, qy, qz);
-          if (d < best) {
-            best = d;
-            best_j = static_cast<int>(j);
-          }
+          offer(kd_sq_dist(static_cast<double>(p.x), static_cast<double>(p.y), static_cast<double>(p.z), qx, qy, qz), static_cast<int>(j));
         }
       } else {
         const double2* __restrict__ pts = static_cast<const double2*>(t.leaf_points);
         for (uint32_t j = first; j < first + cnt; j++) {
           const double2 a = __ldg(pts + 2 * static_cast<size_t>(j)), b = __ldg(pts + 2 * static_cast<size_t>(j) + 1);
-          const double d = kd_sq_dist(a.x, a.y, b.x, qx, qy, qz);
-          if (d < best) {
-            best = d;
-            best_j = static_cast<int>(j);
-          }
+          offer(kd_sq_dist(a.x, a.y, b.x, qx, qy, qz), static_cast<int>(j));
         }
       }
     }
     if (sp == 0) break;
     sp--;
     node_idx = stack_node[sp];
-    cut = stack_cut[sp];
+    bound = stack_bound[sp];
   }
-  *out_sq = best;
-  return best_j;
 }
 
 }  // namespace b2

@@ -14,6 +14,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -81,17 +82,47 @@ __global__ void segment_heads_kernel(size_t n, const uint32_t* __restrict__ flag
   }
 }
 
-// One thread per voxel (id order): sequential float64 accumulation in insertion order, then finalize (divide by count).
-__global__ void accumulate_voxels_kernel(const double* __restrict__ pts, int pstride, const double* __restrict__ covs, int cstride, size_t n, size_t num_voxels,
-                                         double inv_leaf, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_start,
-                                         const uint32_t* __restrict__ seg_of_rank, double* __restrict__ records, int32_t* __restrict__ coords) {
+// One thread per voxel of the inserted batch, in first-touch order r: its integer coordinate and the id it already has in the
+// map (-1: the voxel is new).
+__global__ void batch_voxels_kernel(const double* __restrict__ pts, int pstride, size_t num_batch, double inv_leaf, const uint32_t* __restrict__ idx,
+                                    const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_of_rank, const VoxelBucket* __restrict__ buckets, uint32_t mask,
+                                    size_t num_existing, int32_t* __restrict__ batch_coords, int32_t* __restrict__ existing_id, uint32_t* __restrict__ is_new) {
   const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (r >= num_voxels) return;
+  if (r >= num_batch) return;
+  const double* p0 = pts + static_cast<size_t>(idx[seg_start[seg_of_rank[r]]]) * pstride;
+  int c[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) batch_coords[r * 3 + k] = c[k] = voxel_coord1(p0[k], inv_leaf);
+  const int e = num_existing ? lookup_voxel(buckets, mask, c[0], c[1], c[2]) : -1;
+  existing_id[r] = e;
+  is_new[r] = e < 0 ? 1u : 0u;
+}
+
+// One thread per voxel of the batch: GaussianVoxel::add for each of its points in insertion order, then finalize
+// (src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:23-47).  A voxel that already exists is finalized, so add() first
+// re-opens it (mean *= n, cov *= n); the sums then continue from there one point at a time -- exactly the CPU's float64
+// operation sequence, so means / covariances stay bit-identical over any number of insert() calls.
+__global__ void accumulate_voxels_kernel(const double* __restrict__ pts, int pstride, const double* __restrict__ covs, int cstride, size_t n, size_t num_batch,
+                                         const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_of_rank,
+                                         const int32_t* __restrict__ batch_coords, const int32_t* __restrict__ existing_id, const uint32_t* __restrict__ new_rank,
+                                         size_t num_existing, uint32_t lru_counter, double* __restrict__ records, int32_t* __restrict__ coords, uint32_t* __restrict__ lru) {
+  const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (r >= num_batch) return;
   const uint32_t s = seg_of_rank[r];
   const size_t begin = seg_start[s];
-  const size_t end = (s + 1 < num_voxels) ? seg_start[s + 1] : n;
+  const size_t end = (s + 1 < num_batch) ? seg_start[s + 1] : n;
   const int ld = cstride == 16 ? 4 : 3;
-  double m[3] = {0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0};
+  const int e = existing_id[r];
+  const size_t dest = e >= 0 ? static_cast<size_t>(e) : num_existing + new_rank[r];  // new voxels: first-touch order after the existing ones
+  double* rec = records + dest * kRecordDoubles;
+  double m[3] = {0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0}, cnt0 = 0.0;
+  if (e >= 0) {
+    cnt0 = rec[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) m[k] = __dmul_rn(rec[k], cnt0);
+#pragma unroll
+    for (int k = 0; k < 6; k++) c[k] = __dmul_rn(rec[3 + k], cnt0);
+  }
   for (size_t j = begin; j < end; j++) {
     const size_t i = idx[j];
     const double* p = pts + i * pstride;
@@ -106,16 +137,35 @@ __global__ void accumulate_voxels_kernel(const double* __restrict__ pts, int pst
     c[4] = __dadd_rn(c[4], cv[1 * ld + 2]);
     c[5] = __dadd_rn(c[5], cv[2 * ld + 2]);
   }
-  const double cnt = static_cast<double>(end - begin);
-  double* rec = records + r * kRecordDoubles;
+  const double cnt = cnt0 + static_cast<double>(end - begin);
 #pragma unroll
   for (int k = 0; k < 3; k++) rec[k] = __ddiv_rn(m[k], cnt);
 #pragma unroll
   for (int k = 0; k < 6; k++) rec[3 + k] = __ddiv_rn(c[k], cnt);
   rec[9] = cnt;
-  const double* p0 = pts + static_cast<size_t>(idx[begin]) * pstride;
+  if (e < 0) {
 #pragma unroll
-  for (int k = 0; k < 3; k++) coords[r * 3 + k] = voxel_coord1(p0[k], inv_leaf);
+    for (int k = 0; k < 3; k++) coords[dest * 3 + k] = batch_coords[r * 3 + k];
+  }
+  lru[dest] = lru_counter;  // incremental_voxelmap_impl.hpp:49
+}
+
+// LRU eviction (incremental_voxelmap_impl.hpp:55-66): voxels untouched for more than `horizon` inserts are removed, the
+// survivors keep their relative order (std::remove_if) and are re-indexed.
+__global__ void lru_keep_flags_kernel(const uint32_t* __restrict__ lru, size_t V, uint32_t horizon, uint32_t counter, uint32_t* __restrict__ keep) {
+  const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (r < V) keep[r] = (static_cast<unsigned long long>(lru[r]) + horizon < counter) ? 0u : 1u;
+}
+__global__ void lru_compact_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, size_t V, const double* __restrict__ rec_in, const int32_t* __restrict__ coords_in,
+                                   const uint32_t* __restrict__ lru_in, double* __restrict__ rec_out, int32_t* __restrict__ coords_out, uint32_t* __restrict__ lru_out) {
+  const size_t r = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (r >= V || !keep[r]) return;
+  const size_t d = pos[r];
+#pragma unroll
+  for (int k = 0; k < kRecordDoubles; k++) rec_out[d * kRecordDoubles + k] = rec_in[r * kRecordDoubles + k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) coords_out[d * 3 + k] = coords_in[r * 3 + k];
+  lru_out[d] = lru_in[r];
 }
 
 __global__ void insert_buckets_kernel(const int32_t* __restrict__ coords, size_t num_voxels, VoxelBucket* __restrict__ buckets, uint32_t mask) {
@@ -148,6 +198,37 @@ __global__ void lookup_points_kernel(const double* __restrict__ pts, int pstride
   out[i] = lookup_voxel(buckets, mask, x, y, z);
 }
 
+// overlap_gpu (src/gtsam_points/types/gaussian_voxelmap_gpu_funcs.cu:65-194): a source point counts if, for the FIRST map j in
+// order, T_j p falls into one of its voxels.  float64 with the CPU map's operation order (CPU / GPU agree exactly, where the
+// reference's float32 path promises ~1 %: src/test/test_voxelmap.cpp:231-239).
+struct OverlapMap {
+  const VoxelBucket* buckets;
+  uint32_t mask;
+  uint32_t pad;
+  double inv_leaf;
+  double T[12];  // rows of [R | t]
+};
+template <typename PT>
+__global__ void overlap_kernel(const PT* __restrict__ pts, size_t n, size_t n_pad, const OverlapMap* __restrict__ maps, int num_maps, unsigned long long* __restrict__ count) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  bool hit = false;
+  if (i < n) {
+    const double x = static_cast<double>(pts[i]), y = static_cast<double>(pts[n_pad + i]), z = static_cast<double>(pts[2 * n_pad + i]);
+    for (int j = 0; j < num_maps && !hit; j++) {
+      const OverlapMap& m = maps[j];
+      int c[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double q = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m.T[r * 4 + 0], x), __dmul_rn(m.T[r * 4 + 1], y)), __dmul_rn(m.T[r * 4 + 2], z)), m.T[r * 4 + 3]);
+        c[r] = voxel_coord1(q, m.inv_leaf);
+      }
+      hit = lookup_voxel(m.buckets, m.mask, c[0], c[1], c[2]) >= 0;
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, static_cast<unsigned long long>(__popc(b)));
+}
+
 // load factor <= 0.25 (see b2_device.cuh: one-round-trip lookups)
 size_t bucket_count_for(size_t num_voxels) { return static_cast<size_t>(next_pow2(std::max<uint64_t>(64, 4 * static_cast<uint64_t>(num_voxels)))); }
 
@@ -160,14 +241,72 @@ b2_status alloc_map(b2_ctx* ctx, double resolution, size_t V, b2_voxelmap** out)
   vm->num_buckets = bucket_count_for(V);
   cudaError_t e;
   const size_t vr = std::max<size_t>(V, 1);
+  vm->capacity = vr;
   if ((e = cudaMalloc(reinterpret_cast<void**>(&vm->d_buckets), vm->num_buckets * sizeof(VoxelBucket))) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&vm->d_records), vr * kRecordDoubles * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&vm->d_coords), vr * 3 * sizeof(int32_t))) != cudaSuccess) {
+      (e = cudaMalloc(reinterpret_cast<void**>(&vm->d_coords), vr * 3 * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&vm->d_lru), vr * sizeof(uint32_t))) != cudaSuccess ||
+      (e = cudaMemsetAsync(vm->d_lru, 0, vr * sizeof(uint32_t), ctx->stream)) != cudaSuccess) {
     b2_voxelmap_destroy(vm);
     return fail(B2_ERR_OUT_OF_MEMORY, "voxelmap allocation: %s", cudaGetErrorString(e));
   }
-  vm->device_bytes = vm->num_buckets * sizeof(VoxelBucket) + vr * kRecordDoubles * sizeof(double) + vr * 3 * sizeof(int32_t);
+  vm->device_bytes = vm->num_buckets * sizeof(VoxelBucket) + vr * (kRecordDoubles * sizeof(double) + 3 * sizeof(int32_t) + sizeof(uint32_t));
   *out = vm;
+  return B2_OK;
+}
+
+// grow the per-voxel arrays to hold `want` voxels (contents up to num_voxels are kept)
+b2_status reserve_voxels(b2_voxelmap* vm, size_t want) {
+  if (want <= vm->capacity) return B2_OK;
+  const size_t cap = std::max(want, vm->capacity * 2);
+  cudaStream_t st = vm->ctx->stream;
+  double* rec = nullptr;
+  int32_t* coords = nullptr;
+  uint32_t* lru = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&rec), cap * kRecordDoubles * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&coords), cap * 3 * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&lru), cap * sizeof(uint32_t))) != cudaSuccess) {
+    if (rec) cudaFree(rec);
+    if (coords) cudaFree(coords);
+    return fail(B2_ERR_OUT_OF_MEMORY, "voxelmap growth: %s", cudaGetErrorString(e));
+  }
+  const size_t V = vm->num_voxels;
+  if (V) {
+    cudaMemcpyAsync(rec, vm->d_records, V * kRecordDoubles * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(coords, vm->d_coords, V * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(lru, vm->d_lru, V * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+  }
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) {
+    cudaFree(rec), cudaFree(coords), cudaFree(lru);
+    return fail(B2_ERR_CUDA, "voxelmap growth: %s", cudaGetErrorString(e));
+  }
+  cudaFree(vm->d_records), cudaFree(vm->d_coords), cudaFree(vm->d_lru);
+  vm->d_records = rec, vm->d_coords = coords, vm->d_lru = lru;
+  vm->device_bytes += (cap - vm->capacity) * (kRecordDoubles * sizeof(double) + 3 * sizeof(int32_t) + sizeof(uint32_t));
+  vm->capacity = cap;
+  return B2_OK;
+}
+
+// (re)build the bucket table over the current voxels; resized when the load factor bound asks for it
+b2_status rebuild_table(b2_voxelmap* vm) {
+  cudaStream_t st = vm->ctx->stream;
+  const size_t nb = bucket_count_for(vm->num_voxels);
+  if (nb != vm->num_buckets) {
+    VoxelBucket* fresh = nullptr;
+    B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&fresh), nb * sizeof(VoxelBucket)));
+    cudaStreamSynchronize(st);
+    cudaFree(vm->d_buckets);
+    vm->device_bytes += (nb - vm->num_buckets) * sizeof(VoxelBucket);
+    vm->d_buckets = fresh;
+    vm->num_buckets = nb;
+  }
+  B2_CUDA(cudaMemsetAsync(vm->d_buckets, 0xFF, vm->num_buckets * sizeof(VoxelBucket), st));
+  if (vm->num_voxels) {
+    insert_buckets_kernel<<<static_cast<unsigned>((vm->num_voxels + 127) / 128), 128, 0, st>>>(vm->d_coords, vm->num_voxels, vm->d_buckets, static_cast<uint32_t>(vm->num_buckets / kGroup - 1));
+    B2_CUDA(cudaGetLastError());
+  }
+  vm->generation++;
   return B2_OK;
 }
 
@@ -236,6 +375,158 @@ b2_status b2_voxelmap_create_from_voxels(b2_ctx* ctx, double resolution, const i
   return B2_OK;
 }
 
+b2_status b2_voxelmap_create(b2_ctx* ctx, double resolution, b2_voxelmap** out) {
+  B2_REQUIRE(out != nullptr, "b2_voxelmap_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_voxelmap_create: ctx is NULL");
+  B2_REQUIRE(resolution > 0.0, "b2_voxelmap_create: resolution must be positive");
+  return b2_voxelmap_create_from_voxels(ctx, resolution, nullptr, nullptr, nullptr, nullptr, 0, out);
+}
+
+b2_status b2_voxelmap_set_lru(b2_voxelmap* vm, size_t lru_horizon, size_t lru_clear_cycle) {
+  B2_REQUIRE(vm != nullptr, "b2_voxelmap_set_lru: vm is NULL");
+  B2_REQUIRE(lru_clear_cycle > 0, "b2_voxelmap_set_lru: lru_clear_cycle must be positive");
+  vm->lru_horizon = lru_horizon;  // IncrementalVoxelMap::set_lru_horizon / set_lru_clear_cycle (ann/incremental_voxelmap.hpp)
+  vm->lru_clear_cycle = lru_clear_cycle;
+  return B2_OK;
+}
+
+// IncrementalVoxelMap<GaussianVoxel>::insert (ann/impl/incremental_voxelmap_impl.hpp:31-68) on the device: the batch is
+// segmented into voxels by two stable radix sorts (points of a voxel stay in insertion order, voxels are ranked by first
+// touch), voxels that already exist are found through the table and continued, new ones get the next ids in first-touch
+// order, then the LRU sweep and the table rebuild.  Deterministic; ids, counts, means and covariances equal the CPU map's.
+b2_status b2_voxelmap_insert(b2_voxelmap* vm, const double* points, int point_stride, const double* covs, int cov_stride, size_t n) {
+  B2_REQUIRE(vm != nullptr, "b2_voxelmap_insert: vm is NULL");
+  B2_REQUIRE(point_stride == 3 || point_stride == 4, "b2_voxelmap_insert: point_stride must be 3 or 4");
+  B2_REQUIRE(cov_stride == 9 || cov_stride == 16, "b2_voxelmap_insert: cov_stride must be 9 or 16");
+  B2_REQUIRE(n == 0 || (points && covs), "error: points/covs have not been allocated!!");  // GaussianVoxel::add reads covs
+  B2_REQUIRE(n < (1ull << 31), "b2_voxelmap_insert: at most 2^31-1 points per insert");
+  b2_ctx* ctx = vm->ctx;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const double inv_leaf = vm->inv_resolution;
+  const size_t V_old = vm->num_voxels;
+
+  if (n > 0) {
+    DevBuf raw_p, raw_c, key_z, key_z2, idx_a, idx_b, key_xy, key_xy2, flags, seg_incl, tmp;
+    B2_CUDA(cudaMalloc(&raw_p.p, n * point_stride * sizeof(double)));
+    B2_CUDA(cudaMalloc(&raw_c.p, n * cov_stride * sizeof(double)));
+    B2_CUDA(cudaMemcpyAsync(raw_p.p, points, n * point_stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(raw_c.p, covs, n * cov_stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMalloc(&key_z.p, n * 4));
+    B2_CUDA(cudaMalloc(&key_z2.p, n * 4));
+    B2_CUDA(cudaMalloc(&idx_a.p, n * 4));
+    B2_CUDA(cudaMalloc(&idx_b.p, n * 4));
+    B2_CUDA(cudaMalloc(&key_xy.p, n * 8));
+    B2_CUDA(cudaMalloc(&key_xy2.p, n * 8));
+    B2_CUDA(cudaMalloc(&flags.p, n * 4));
+    B2_CUDA(cudaMalloc(&seg_incl.p, n * 4));
+
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    const double* rp = raw_p.as<double>();
+    const double* rc = raw_c.as<double>();
+    const int ni = static_cast<int>(n);
+
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, key_z.as<uint32_t>(), key_z2.as<uint32_t>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), ni, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, key_xy.as<unsigned long long>(), key_xy2.as<unsigned long long>(), idx_b.as<uint32_t>(), idx_a.as<uint32_t>(), ni, 0, 64, st);
+    cub::DeviceScan::InclusiveSum(nullptr, t3, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), ni, st);
+    const size_t tmp_bytes = std::max(std::max(t1, t2), std::max(t3, static_cast<size_t>(16)));
+    B2_CUDA(cudaMalloc(&tmp.p, tmp_bytes));
+
+    // pass 1: stable sort by z; pass 2: stable sort by (x, y)  => lexicographic (x, y, z), insertion order inside a voxel
+    point_coord_keys_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, key_z.as<uint32_t>(), idx_a.as<uint32_t>());
+    size_t tb = tmp_bytes;
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_z.as<uint32_t>(), key_z2.as<uint32_t>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), ni, 0, 32, st));
+    gather_xy_keys_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, idx_b.as<uint32_t>(), key_xy.as<unsigned long long>());
+    tb = tmp_bytes;
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_xy.as<unsigned long long>(), key_xy2.as<unsigned long long>(), idx_b.as<uint32_t>(), idx_a.as<uint32_t>(), ni, 0, 64, st));
+    const uint32_t* idx = idx_a.as<uint32_t>();
+
+    head_flags_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, idx, flags.as<uint32_t>());
+    tb = tmp_bytes;
+    B2_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), ni, st));
+    uint32_t B32 = 0;
+    B2_CUDA(cudaMemcpyAsync(&B32, seg_incl.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const size_t B = B32;  // voxels touched by this batch
+
+    DevBuf seg_start, seg_first, seg_first2, seg_iota, seg_of_rank, tmp2, batch_coords, existing_id, is_new, new_rank;
+    B2_CUDA(cudaMalloc(&seg_start.p, B * 4));
+    B2_CUDA(cudaMalloc(&seg_first.p, B * 4));
+    B2_CUDA(cudaMalloc(&seg_first2.p, B * 4));
+    B2_CUDA(cudaMalloc(&seg_iota.p, B * 4));
+    B2_CUDA(cudaMalloc(&seg_of_rank.p, B * 4));
+    B2_CUDA(cudaMalloc(&batch_coords.p, B * 12));
+    B2_CUDA(cudaMalloc(&existing_id.p, B * 4));
+    B2_CUDA(cudaMalloc(&is_new.p, B * 4));
+    B2_CUDA(cudaMalloc(&new_rank.p, B * 4));
+    segment_heads_kernel<<<grid, 256, 0, st>>>(n, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), idx, seg_start.as<uint32_t>(), seg_first.as<uint32_t>(), seg_iota.as<uint32_t>());
+    size_t t4 = 0, t5 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t4, seg_first.as<uint32_t>(), seg_first2.as<uint32_t>(), seg_iota.as<uint32_t>(), seg_of_rank.as<uint32_t>(), static_cast<int>(B), 0, 32, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, t5, is_new.as<uint32_t>(), new_rank.as<uint32_t>(), static_cast<int>(B), st);
+    size_t tb2 = std::max<size_t>(std::max(t4, t5), 16);
+    B2_CUDA(cudaMalloc(&tmp2.p, tb2));
+    size_t tbb = tb2;
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tbb, seg_first.as<uint32_t>(), seg_first2.as<uint32_t>(), seg_iota.as<uint32_t>(), seg_of_rank.as<uint32_t>(), static_cast<int>(B), 0, 32, st));
+
+    const unsigned vgrid = static_cast<unsigned>((B + 127) / 128);
+    batch_voxels_kernel<<<vgrid, 128, 0, st>>>(rp, point_stride, B, inv_leaf, idx, seg_start.as<uint32_t>(), seg_of_rank.as<uint32_t>(), vm->d_buckets,
+                                               static_cast<uint32_t>(vm->num_buckets / kGroup - 1), V_old, batch_coords.as<int32_t>(), existing_id.as<int32_t>(), is_new.as<uint32_t>());
+    tbb = tb2;
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, tbb, is_new.as<uint32_t>(), new_rank.as<uint32_t>(), static_cast<int>(B), st));
+    uint32_t last_rank = 0, last_new = 0;
+    B2_CUDA(cudaMemcpyAsync(&last_rank, new_rank.as<uint32_t>() + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&last_new, is_new.as<uint32_t>() + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const size_t num_new = static_cast<size_t>(last_rank) + last_new;
+    B2_REQUIRE(V_old + num_new < (1ull << 30), "b2_voxelmap_insert: too many voxels");
+    B2_TRY(reserve_voxels(vm, V_old + num_new));
+    accumulate_voxels_kernel<<<vgrid, 128, 0, st>>>(rp, point_stride, rc, cov_stride, n, B, idx, seg_start.as<uint32_t>(), seg_of_rank.as<uint32_t>(), batch_coords.as<int32_t>(),
+                                                    existing_id.as<int32_t>(), new_rank.as<uint32_t>(), V_old, static_cast<uint32_t>(vm->lru_counter), vm->d_records, vm->d_coords,
+                                                    vm->d_lru);
+    B2_CUDA(cudaGetLastError());
+    vm->num_voxels = V_old + num_new;
+    B2_CUDA(cudaStreamSynchronize(st));  // the scratch buffers above are released at scope exit
+  }
+
+  // incremental_voxelmap_impl.hpp:55-66: every lru_clear_cycle-th insert evicts voxels not touched within lru_horizon inserts
+  vm->lru_counter++;
+  if (vm->lru_counter % vm->lru_clear_cycle == 0 && vm->num_voxels > 0) {
+    const size_t V = vm->num_voxels;
+    DevBuf keep, pos, tmp3, rec2, coords2, lru2;
+    B2_CUDA(cudaMalloc(&keep.p, V * 4));
+    B2_CUDA(cudaMalloc(&pos.p, V * 4));
+    const unsigned g = static_cast<unsigned>((V + 255) / 256);
+    lru_keep_flags_kernel<<<g, 256, 0, st>>>(vm->d_lru, V, static_cast<uint32_t>(vm->lru_horizon), static_cast<uint32_t>(vm->lru_counter), keep.as<uint32_t>());
+    size_t t6 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t6, keep.as<uint32_t>(), pos.as<uint32_t>(), static_cast<int>(V), st);
+    B2_CUDA(cudaMalloc(&tmp3.p, std::max<size_t>(t6, 16)));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(tmp3.p, t6, keep.as<uint32_t>(), pos.as<uint32_t>(), static_cast<int>(V), st));
+    uint32_t last_pos = 0, last_keep = 0;
+    B2_CUDA(cudaMemcpyAsync(&last_pos, pos.as<uint32_t>() + (V - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&last_keep, keep.as<uint32_t>() + (V - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const size_t kept = static_cast<size_t>(last_pos) + last_keep;
+    if (kept != V) {
+      const size_t cap = vm->capacity;
+      B2_CUDA(cudaMalloc(&rec2.p, cap * kRecordDoubles * sizeof(double)));
+      B2_CUDA(cudaMalloc(&coords2.p, cap * 3 * sizeof(int32_t)));
+      B2_CUDA(cudaMalloc(&lru2.p, cap * sizeof(uint32_t)));
+      lru_compact_kernel<<<g, 256, 0, st>>>(keep.as<uint32_t>(), pos.as<uint32_t>(), V, vm->d_records, vm->d_coords, vm->d_lru, rec2.as<double>(), coords2.as<int32_t>(), lru2.as<uint32_t>());
+      B2_CUDA(cudaGetLastError());
+      B2_CUDA(cudaStreamSynchronize(st));
+      std::swap(vm->d_records, *reinterpret_cast<double**>(&rec2.p));
+      std::swap(vm->d_coords, *reinterpret_cast<int32_t**>(&coords2.p));
+      std::swap(vm->d_lru, *reinterpret_cast<uint32_t**>(&lru2.p));
+      vm->num_voxels = kept;
+    }
+  }
+  B2_TRY(rebuild_table(vm));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B2_OK;
+}
+
 b2_status b2_voxelmap_create_from_points(b2_ctx* ctx, double resolution, const double* points, int point_stride, const double* covs, int cov_stride,
                                          size_t n, b2_voxelmap** out) {
   B2_REQUIRE(out != nullptr, "b2_voxelmap_create_from_points: out is NULL");
@@ -246,84 +537,12 @@ b2_status b2_voxelmap_create_from_points(b2_ctx* ctx, double resolution, const d
   B2_REQUIRE(cov_stride == 9 || cov_stride == 16, "b2_voxelmap_create_from_points: cov_stride must be 9 or 16");
   B2_REQUIRE(n == 0 || (points && covs), "b2_voxelmap_create_from_points: points and covs are required");  // reference: GaussianVoxel::add reads covs
   B2_REQUIRE(n < (1ull << 31), "b2_voxelmap_create_from_points: at most 2^31-1 points");
-  B2_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const double inv_leaf = 1.0 / resolution;
-
-  if (n == 0) {
-    return b2_voxelmap_create_from_voxels(ctx, resolution, nullptr, nullptr, nullptr, nullptr, 0, out);
-  }
-
-  DevBuf raw_p, raw_c, key_z, key_z2, idx_a, idx_b, key_xy, key_xy2, flags, seg_incl, tmp;
-  B2_CUDA(cudaMalloc(&raw_p.p, n * point_stride * sizeof(double)));
-  B2_CUDA(cudaMalloc(&raw_c.p, n * cov_stride * sizeof(double)));
-  B2_CUDA(cudaMemcpyAsync(raw_p.p, points, n * point_stride * sizeof(double), cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMemcpyAsync(raw_c.p, covs, n * cov_stride * sizeof(double), cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMalloc(&key_z.p, n * 4));
-  B2_CUDA(cudaMalloc(&key_z2.p, n * 4));
-  B2_CUDA(cudaMalloc(&idx_a.p, n * 4));
-  B2_CUDA(cudaMalloc(&idx_b.p, n * 4));
-  B2_CUDA(cudaMalloc(&key_xy.p, n * 8));
-  B2_CUDA(cudaMalloc(&key_xy2.p, n * 8));
-  B2_CUDA(cudaMalloc(&flags.p, n * 4));
-  B2_CUDA(cudaMalloc(&seg_incl.p, n * 4));
-
-  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-  const double* rp = raw_p.as<double>();
-  const double* rc = raw_c.as<double>();
-  const int ni = static_cast<int>(n);
-
-  size_t t1 = 0, t2 = 0, t3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t1, key_z.as<uint32_t>(), key_z2.as<uint32_t>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), ni, 0, 32, st);
-  cub::DeviceRadixSort::SortPairs(nullptr, t2, key_xy.as<unsigned long long>(), key_xy2.as<unsigned long long>(), idx_b.as<uint32_t>(), idx_a.as<uint32_t>(), ni, 0, 64, st);
-  cub::DeviceScan::InclusiveSum(nullptr, t3, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), ni, st);
-  const size_t tmp_bytes = std::max(std::max(t1, t2), std::max(t3, static_cast<size_t>(16)));
-  B2_CUDA(cudaMalloc(&tmp.p, tmp_bytes));
-
-  // pass 1: stable sort by z; pass 2: stable sort by (x, y)  => lexicographic (x, y, z), insertion order inside a voxel
-  point_coord_keys_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, key_z.as<uint32_t>(), idx_a.as<uint32_t>());
-  size_t tb = tmp_bytes;
-  B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_z.as<uint32_t>(), key_z2.as<uint32_t>(), idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), ni, 0, 32, st));
-  gather_xy_keys_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, idx_b.as<uint32_t>(), key_xy.as<unsigned long long>());
-  tb = tmp_bytes;
-  B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_xy.as<unsigned long long>(), key_xy2.as<unsigned long long>(), idx_b.as<uint32_t>(), idx_a.as<uint32_t>(), ni, 0, 64, st));
-  const uint32_t* idx = idx_a.as<uint32_t>();
-
-  head_flags_kernel<<<grid, 256, 0, st>>>(rp, point_stride, n, inv_leaf, idx, flags.as<uint32_t>());
-  tb = tmp_bytes;
-  B2_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), ni, st));
-  uint32_t V32 = 0;
-  B2_CUDA(cudaMemcpyAsync(&V32, seg_incl.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaStreamSynchronize(st));
-  const size_t V = V32;
-
-  DevBuf seg_start, seg_first, seg_first2, seg_iota, seg_of_rank, tmp2;
-  B2_CUDA(cudaMalloc(&seg_start.p, V * 4));
-  B2_CUDA(cudaMalloc(&seg_first.p, V * 4));
-  B2_CUDA(cudaMalloc(&seg_first2.p, V * 4));
-  B2_CUDA(cudaMalloc(&seg_iota.p, V * 4));
-  B2_CUDA(cudaMalloc(&seg_of_rank.p, V * 4));
-  segment_heads_kernel<<<grid, 256, 0, st>>>(n, flags.as<uint32_t>(), seg_incl.as<uint32_t>(), idx, seg_start.as<uint32_t>(), seg_first.as<uint32_t>(),
-                                             seg_iota.as<uint32_t>());
-  size_t t4 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, t4, seg_first.as<uint32_t>(), seg_first2.as<uint32_t>(), seg_iota.as<uint32_t>(), seg_of_rank.as<uint32_t>(), static_cast<int>(V), 0, 32, st);
-  B2_CUDA(cudaMalloc(&tmp2.p, std::max<size_t>(t4, 16)));
-  B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, t4, seg_first.as<uint32_t>(), seg_first2.as<uint32_t>(), seg_iota.as<uint32_t>(), seg_of_rank.as<uint32_t>(), static_cast<int>(V), 0, 32, st));
-
   b2_voxelmap* vm = nullptr;
-  B2_TRY(alloc_map(ctx, resolution, V, &vm));
-  cudaError_t e;
-  const unsigned vgrid = static_cast<unsigned>((V + 127) / 128);
-  accumulate_voxels_kernel<<<vgrid, 128, 0, st>>>(rp, point_stride, rc, cov_stride, n, V, inv_leaf, idx, seg_start.as<uint32_t>(), seg_of_rank.as<uint32_t>(),
-                                                  vm->d_records, vm->d_coords);
-  if ((e = cudaMemsetAsync(vm->d_buckets, 0xFF, vm->num_buckets * sizeof(VoxelBucket), st)) != cudaSuccess) {
+  B2_TRY(b2_voxelmap_create(ctx, resolution, &vm));
+  const b2_status st = b2_voxelmap_insert(vm, points, point_stride, covs, cov_stride, n);  // the one-shot build IS the first insert
+  if (st != B2_OK) {
     b2_voxelmap_destroy(vm);
-    return fail(B2_ERR_CUDA, "b2_voxelmap_create_from_points: %s", cudaGetErrorString(e));
-  }
-  insert_buckets_kernel<<<vgrid, 128, 0, st>>>(vm->d_coords, V, vm->d_buckets, static_cast<uint32_t>(vm->num_buckets / kGroup - 1));
-  if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) {
-    b2_voxelmap_destroy(vm);
-    return fail(B2_ERR_CUDA, "b2_voxelmap_create_from_points: %s", cudaGetErrorString(e));
+    return st;
   }
   *out = vm;
   return B2_OK;
@@ -335,6 +554,7 @@ b2_status b2_voxelmap_destroy(b2_voxelmap* vm) {
   if (vm->d_buckets) cudaFree(vm->d_buckets);
   if (vm->d_records) cudaFree(vm->d_records);
   if (vm->d_coords) cudaFree(vm->d_coords);
+  if (vm->d_lru) cudaFree(vm->d_lru);
   delete vm;
   return B2_OK;
 }
@@ -373,6 +593,119 @@ b2_status b2_voxelmap_download(const b2_voxelmap* vm, int32_t* coords, double* m
     }
     if (num_points) num_points[r] = static_cast<int32_t>(q[9]);
   }
+  return B2_OK;
+}
+
+// ---- save_compact / load: the reference's wire format (types/gaussian_voxel_data.hpp:11-54, gaussian_voxelmap_cpu.cpp:79-135) ----
+namespace {
+struct GaussianVoxelData {  // 56 bytes, as in the reference
+  int32_t coord[3];
+  int32_t num_points;
+  float mean[3];
+  float cov[6];  // 00, 01, 02, 11, 12, 22
+  float intensity;
+};
+static_assert(sizeof(GaussianVoxelData) == 56, "GaussianVoxelData layout");
+}  // namespace
+
+b2_status b2_voxelmap_save_compact(const b2_voxelmap* vm, const char* path) {
+  B2_REQUIRE(vm && path, "b2_voxelmap_save_compact: NULL argument");
+  const size_t V = vm->num_voxels;
+  std::vector<int32_t> coords(V * 3), cnt(V);
+  std::vector<double> means(V * 3), covs(V * 9);
+  B2_TRY(b2_voxelmap_download(vm, coords.data(), means.data(), covs.data(), cnt.data()));
+  std::vector<GaussianVoxelData> serial(V);
+  for (size_t r = 0; r < V; r++) {
+    GaussianVoxelData& d = serial[r];
+    for (int k = 0; k < 3; k++) d.coord[k] = coords[r * 3 + k], d.mean[k] = static_cast<float>(means[r * 3 + k]);
+    d.num_points = cnt[r];
+    const double* c = &covs[r * 9];
+    d.cov[0] = static_cast<float>(c[0]), d.cov[1] = static_cast<float>(c[1]), d.cov[2] = static_cast<float>(c[2]);
+    d.cov[3] = static_cast<float>(c[4]), d.cov[4] = static_cast<float>(c[5]), d.cov[5] = static_cast<float>(c[8]);
+    d.intensity = 0.0f;  // intensities are not part of the scan-matching path
+  }
+  std::FILE* fp = std::fopen(path, "wb");
+  if (!fp) return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_save_compact: cannot open %s", path);
+  std::fprintf(fp, "compact 1\nresolution %g\nlru_count %zu\nlru_cycle %zu\nlru_thresh %zu\nvoxel_bytes %zu\nnum_voxels %zu\n", vm->resolution, vm->lru_counter, vm->lru_clear_cycle,
+               vm->lru_horizon, sizeof(GaussianVoxelData), V);
+  const bool ok = std::fwrite(serial.data(), sizeof(GaussianVoxelData), V, fp) == V;
+  std::fclose(fp);
+  if (!ok) return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_save_compact: short write to %s", path);
+  return B2_OK;
+}
+
+b2_status b2_voxelmap_load(b2_ctx* ctx, const char* path, b2_voxelmap** out) {
+  B2_REQUIRE(out != nullptr, "b2_voxelmap_load: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx && path, "b2_voxelmap_load: NULL argument");
+  std::FILE* fp = std::fopen(path, "rb");
+  if (!fp) return fail(B2_ERR_INVALID_ARGUMENT, "error: failed to open %s", path);  // gaussian_voxelmap_cpu.cpp:100-103
+  char tok[64];
+  int compact = 0;
+  double resolution = 1.0;
+  size_t lru_count = 0, lru_cycle = 0, lru_thresh = 0, voxel_bytes = 0, V = 0;
+  const int got = std::fscanf(fp, "%63s %d %63s %lf %63s %zu %63s %zu %63s %zu %63s %zu %63s %zu", tok, &compact, tok, &resolution, tok, &lru_count, tok, &lru_cycle, tok, &lru_thresh,
+                              tok, &voxel_bytes, tok, &V);
+  if (got != 14 || voxel_bytes != sizeof(GaussianVoxelData) || !(resolution > 0.0)) {
+    std::fclose(fp);
+    return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_load: %s is not a compact voxel map (header fields %d, voxel_bytes %zu)", path, got, voxel_bytes);
+  }
+  int ch;
+  while ((ch = std::fgetc(fp)) != EOF && ch != '\n') {
+  }
+  std::vector<GaussianVoxelData> serial(V);
+  const size_t rd = std::fread(serial.data(), sizeof(GaussianVoxelData), V, fp);
+  std::fclose(fp);
+  if (rd != V) return fail(B2_ERR_INVALID_ARGUMENT, "b2_voxelmap_load: %s is truncated (%zu of %zu voxels)", path, rd, V);
+  std::vector<int32_t> coords(V * 3), cnt(V);
+  std::vector<double> means(V * 3), covs(V * 9);
+  for (size_t r = 0; r < V; r++) {  // GaussianVoxelData::uncompact (gaussian_voxel_data.hpp:27-46)
+    const GaussianVoxelData& d = serial[r];
+    for (int k = 0; k < 3; k++) coords[r * 3 + k] = d.coord[k], means[r * 3 + k] = d.mean[k];
+    cnt[r] = d.num_points;
+    double* c = &covs[r * 9];
+    c[0] = d.cov[0], c[1] = c[3] = d.cov[1], c[2] = c[6] = d.cov[2], c[4] = d.cov[3], c[5] = c[7] = d.cov[4], c[8] = d.cov[5];
+  }
+  B2_TRY(b2_voxelmap_create_from_voxels(ctx, resolution, coords.data(), means.data(), covs.data(), cnt.data(), V, out));
+  (*out)->lru_counter = lru_count, (*out)->lru_clear_cycle = lru_cycle ? lru_cycle : 10, (*out)->lru_horizon = lru_thresh;
+  return B2_OK;
+}
+
+b2_status b2_overlap(const b2_voxelmap* const* targets, size_t num_targets, const b2_cloud* source, const double* Ts_target_source, double* out_overlap) {
+  B2_REQUIRE(targets && source && Ts_target_source && out_overlap && num_targets > 0, "b2_overlap: NULL / empty argument");
+  B2_REQUIRE(source->d_points != nullptr, "error: source points have not been allocated!!");
+  b2_ctx* ctx = source->ctx;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::vector<OverlapMap> maps(num_targets);
+  for (size_t j = 0; j < num_targets; j++) {
+    B2_REQUIRE(targets[j] != nullptr, "error: Failed to cast target voxelmap to GaussianVoxelMapGPU!!");  // gaussian_voxelmap_gpu_funcs.cu:70-75
+    B2_REQUIRE(targets[j]->ctx->device == ctx->device, "b2_overlap: map %zu lives on another device", j);
+    maps[j].buckets = targets[j]->d_buckets;
+    maps[j].mask = static_cast<uint32_t>(targets[j]->num_buckets / kGroup - 1);
+    maps[j].pad = 0;
+    maps[j].inv_leaf = targets[j]->inv_resolution;
+    std::memcpy(maps[j].T, Ts_target_source + 16 * j, 12 * sizeof(double));
+  }
+  if (source->n == 0) {
+    *out_overlap = 0.0;
+    return B2_OK;
+  }
+  DevBuf d_maps, d_count;
+  B2_CUDA(cudaMalloc(&d_maps.p, maps.size() * sizeof(OverlapMap)));
+  B2_CUDA(cudaMalloc(&d_count.p, sizeof(unsigned long long)));
+  B2_CUDA(cudaMemcpyAsync(d_maps.p, maps.data(), maps.size() * sizeof(OverlapMap), cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
+  const unsigned grid = static_cast<unsigned>((source->n + 255) / 256);
+  if (source->point_bytes == 4)
+    overlap_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(source->d_points), source->n, source->n_pad, d_maps.as<OverlapMap>(), static_cast<int>(num_targets), d_count.as<unsigned long long>());
+  else
+    overlap_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(source->d_points), source->n, source->n_pad, d_maps.as<OverlapMap>(), static_cast<int>(num_targets), d_count.as<unsigned long long>());
+  B2_CUDA(cudaGetLastError());
+  unsigned long long cnt = 0;
+  B2_CUDA(cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  *out_overlap = static_cast<double>(cnt) / static_cast<double>(source->n);  // gaussian_voxelmap_cpu_funcs.cpp:142
   return B2_OK;
 }
 

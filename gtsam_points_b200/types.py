@@ -120,23 +120,46 @@ class GaussianVoxelMapGPU:
         self.ctx = ctx or default_context()
         self._resolution = float(resolution)
         self.h = None
+        self._lru = None
 
     def voxel_resolution(self) -> float:
         return self._resolution
 
     def insert(self, frame: PointCloud):
-        """One-shot build (the reference's GPU map does not support incremental insertion either:
-        include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:63)."""
-        if self.h is not None:
-            raise RuntimeError("GaussianVoxelMapGPU.insert: incremental insertion is not supported on the GPU")
+        """GaussianVoxelMap::insert(const PointCloud&).  The first call builds the map; further calls are incremental with the
+        CPU map's semantics (IncrementalVoxelMap::insert + LRU eviction, ann/impl/incremental_voxelmap_impl.hpp:31-68) -- the
+        reference's own GPU map is one-shot only (types/gaussian_voxelmap_gpu.hpp:63)."""
         if frame.covs is None:
             raise ValueError("GaussianVoxelMapGPU.insert: the frame has no covariances")
-        h = C.c_void_p()
         cov_stride = 9 if frame.covs.shape[1:] == (3, 3) else 16
-        capi.check(
-            capi.lib().b2_voxelmap_create_from_points(self.ctx.h, self._resolution, capi.dptr(frame.points), frame.points.shape[1], capi.dptr(frame.covs), cov_stride, len(frame.points), C.byref(h))
-        )
+        if self.h is None:
+            h = C.c_void_p()
+            capi.check(capi.lib().b2_voxelmap_create(self.ctx.h, self._resolution, C.byref(h)))
+            self.h = h
+            if self._lru is not None:
+                capi.check(capi.lib().b2_voxelmap_set_lru(self.h, *self._lru))
+        capi.check(capi.lib().b2_voxelmap_insert(self.h, capi.dptr(frame.points), frame.points.shape[1], capi.dptr(frame.covs), cov_stride, len(frame.points)))
+
+    def set_lru(self, lru_horizon: int, lru_clear_cycle: int):
+        """IncrementalVoxelMap::set_lru_horizon / set_lru_clear_cycle (ann/incremental_voxelmap.hpp); defaults 10 / 10."""
+        self._lru = (int(lru_horizon), int(lru_clear_cycle))
+        if self.h is not None:
+            capi.check(capi.lib().b2_voxelmap_set_lru(self.h, *self._lru))
+
+    def save_compact(self, path):
+        """GaussianVoxelMapCPU::save_compact wire format (src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:79-97)."""
+        capi.check(capi.lib().b2_voxelmap_save_compact(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, ctx: Context | None = None):
+        """GaussianVoxelMapCPU::load / GaussianVoxelMapGPU::load: reads a save_compact file onto the device."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        capi.check(capi.lib().b2_voxelmap_load(ctx.h, str(path).encode(), C.byref(h)))
+        self = cls(1.0, ctx)
         self.h = h
+        self._resolution = float(self.info().resolution)
+        return self
 
     @classmethod
     def from_voxels(cls, resolution, coords, means, covs, num_points=None, ctx: Context | None = None):
@@ -190,6 +213,18 @@ class GaussianVoxelMapGPU:
             pass
 
 
+def overlap_gpu(targets, source: PointCloud, Ts_target_source) -> float:
+    """overlap_gpu (include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:116-125): fraction of source points p for which
+    T_j p falls into a voxel of target j for some j.  `targets` / `Ts_target_source`: one map + one 4x4, or equally long lists."""
+    if isinstance(targets, GaussianVoxelMapGPU):
+        targets, Ts_target_source = [targets], [Ts_target_source]
+    Ts = np.ascontiguousarray(np.asarray(Ts_target_source, dtype=np.float64).reshape(len(targets), 16))
+    arr = (C.c_void_p * len(targets))(*[t.h for t in targets])
+    out = C.c_double()
+    capi.check(capi.lib().b2_overlap(arr, len(targets), source.h, capi.dptr(Ts), C.cast(C.byref(out), C.POINTER(C.c_double))))
+    return out.value
+
+
 class KdTree:
     """NearestNeighborSearch over a point set, exact 1-NN on the device."""
 
@@ -201,16 +236,40 @@ class KdTree:
         self.h = h
 
     def knn_search(self, queries, k: int = 1, max_sq_dist: float = np.finfo(np.float64).max):
-        """Batched knn_search(pt, 1, ...): returns (indices int64 [-1 = none], squared distances)."""
-        if k != 1:
-            raise NotImplementedError("the device kd-tree answers k = 1 (the GICP correspondence search)")
+        """Batched NearestNeighborSearch::knn_search (ann/nearest_neighbor_search.hpp:31-35): indices int64 and squared
+        distances, sorted by distance; slots beyond the number found hold (-1, max_sq_dist) (ann/knn_result.hpp:44-72).
+        k = 1 returns 1-D arrays, k > 1 arrays of shape (nq, k)."""
         q = np.ascontiguousarray(queries, dtype=np.float64)
         if q.ndim == 1:
             q = q[None]
-        idx = np.zeros(len(q), dtype=np.int64)
-        sqd = np.zeros(len(q))
-        capi.check(capi.lib().b2_kdtree_knn1(self.h, capi.dptr(q), q.shape[1], len(q), float(max_sq_dist), idx.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(sqd)))
+        if k == 1:
+            idx = np.zeros(len(q), dtype=np.int64)
+            sqd = np.zeros(len(q))
+            capi.check(capi.lib().b2_kdtree_knn1(self.h, capi.dptr(q), q.shape[1], len(q), float(max_sq_dist), idx.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(sqd)))
+            return idx, sqd
+        idx = np.zeros((len(q), k), dtype=np.int64)
+        sqd = np.zeros((len(q), k))
+        capi.check(capi.lib().b2_kdtree_knn(self.h, capi.dptr(q), q.shape[1], len(q), int(k), float(max_sq_dist), idx.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(sqd)))
         return idx, sqd
+
+    def radius_search(self, query, radius: float, max_num_neighbors: int = 2**31 - 1):
+        """NearestNeighborSearch::radius_search (ann/nearest_neighbor_search.hpp:45-56) for one query point."""
+        k = 16
+        while True:
+            kk = min(k, max_num_neighbors, 64)
+            idx, sqd = self.knn_search(np.asarray(query, dtype=np.float64)[None], max(kk, 2), radius * radius)
+            idx, sqd = idx[0][:kk], sqd[0][:kk]
+            found = int((idx >= 0).sum())
+            if found < kk or kk == max_num_neighbors or kk >= 64:
+                return idx[:found], sqd[:found]
+            k *= 2
+
+    def estimate_covariances(self, k_neighbors: int = 10, eigen_values=(1e-3, 1.0, 1.0)) -> np.ndarray:
+        """estimate_covariances over this tree's points (src/gtsam_points/features/covariance_estimation.cpp:18-77) -> n x 3 x 3."""
+        out = np.zeros((len(self.points), 3, 3))
+        ev = np.ascontiguousarray(eigen_values, dtype=np.float64)
+        capi.check(capi.lib().b2_kdtree_estimate_covariances(self.h, int(k_neighbors), capi.dptr(ev), capi.dptr(out)))
+        return out
 
     def __del__(self):
         try:
@@ -219,3 +278,14 @@ class KdTree:
                 self.h = None
         except Exception:
             pass
+
+
+def estimate_covariances(points, k_neighbors: int = 10, eigen_values=(1e-3, 1.0, 1.0), ctx: Context | None = None) -> np.ndarray:
+    """gtsam_points::estimate_covariances(points, k_neighbors, eigen_values) on the device (features/covariance_estimation.hpp:41-66):
+    k-NN over a kd-tree built on the spot, covariance of the neighbourhood, EIG regularisation.  Returns n x 3 x 3."""
+    ctx = ctx or default_context()
+    p = np.ascontiguousarray(points.points if isinstance(points, PointCloud) else points, dtype=np.float64)
+    out = np.zeros((len(p), 3, 3))
+    ev = np.ascontiguousarray(eigen_values, dtype=np.float64)
+    capi.check(capi.lib().b2_estimate_covariances(ctx.h, capi.dptr(p), p.shape[1], len(p), int(k_neighbors), capi.dptr(ev), capi.dptr(out)))
+    return out

@@ -110,6 +110,13 @@ B2_API b2_status b2_ctx_create(int device, void* stream, b2_ctx** out);
 B2_API b2_status b2_ctx_destroy(b2_ctx* ctx);
 B2_API b2_status b2_ctx_synchronize(b2_ctx* ctx);
 B2_API void* b2_ctx_stream(b2_ctx* ctx);
+/* Plain device memory on the context's device, for callers above the ABI that own result / exchange buffers without a CUDA
+ * toolchain of their own (the reference keeps such blobs in thrust::device_vector, cuda/nonlinear_factor_set_gpu.hpp:110-118).
+ * b2_memcpy_*: stream-ordered on the context's stream, then synchronised. */
+B2_API b2_status b2_device_malloc(b2_ctx* ctx, size_t bytes, void** out);
+B2_API b2_status b2_device_free(b2_ctx* ctx, void* ptr);
+B2_API b2_status b2_memcpy_d2h(b2_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
+B2_API b2_status b2_memcpy_h2d(b2_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Point clouds.  Replaces PointCloudGPU's upload of points/covs (src/gtsam_points/types/point_cloud_gpu.cu)
@@ -130,6 +137,15 @@ B2_API b2_status b2_cloud_get_info(const b2_cloud* cloud, b2_cloud_info* info);
  * (include/gtsam_points/types/gaussian_voxelmap.hpp:27; CPU semantics ann/impl/incremental_voxelmap_impl.hpp:31-68). */
 B2_API b2_status b2_voxelmap_create_from_points(b2_ctx* ctx, double resolution, const double* points, int point_stride, const double* covs,
                                                 int cov_stride, size_t n, b2_voxelmap** out);
+/* Incremental form: an empty map, then any number of insert() calls -- IncrementalVoxelMap<GaussianVoxel>::insert with its LRU
+ * eviction (include/gtsam_points/ann/impl/incremental_voxelmap_impl.hpp:31-68; defaults lru_horizon = lru_clear_cycle = 10):
+ * voxels that exist are continued (re-opened, summed on, re-finalized), new voxels get the next ids in first-touch order,
+ * every lru_clear_cycle-th insert removes the voxels untouched for more than lru_horizon inserts and re-indexes the rest.
+ * Ids, counts, means and covariances equal the CPU map's after every call.  (The reference's GPU map is one-shot only,
+ * types/gaussian_voxelmap_gpu.hpp:63.)  Factors / factor sets built over the map see the new contents at their next call. */
+B2_API b2_status b2_voxelmap_create(b2_ctx* ctx, double resolution, b2_voxelmap** out);
+B2_API b2_status b2_voxelmap_set_lru(b2_voxelmap* vm, size_t lru_horizon, size_t lru_clear_cycle);
+B2_API b2_status b2_voxelmap_insert(b2_voxelmap* vm, const double* points, int point_stride, const double* covs, int cov_stride, size_t n);
 /* Upload an existing map (e.g. a GaussianVoxelMapCPU's flat_voxels or a save_compact file,
  * include/gtsam_points/types/gaussian_voxel_data.hpp:11-54): coords V x 3, means V x 3, covs V x 9, num_points V. */
 B2_API b2_status b2_voxelmap_create_from_voxels(b2_ctx* ctx, double resolution, const int32_t* coords, const double* means, const double* covs,
@@ -138,6 +154,16 @@ B2_API b2_status b2_voxelmap_destroy(b2_voxelmap* vm);
 B2_API b2_status b2_voxelmap_get_info(const b2_voxelmap* vm, b2_voxelmap_info* info);
 /* download_voxel_means / _covs / _num_points / buckets (gaussian_voxelmap_gpu.hpp:110-114); any pointer may be NULL */
 B2_API b2_status b2_voxelmap_download(const b2_voxelmap* vm, int32_t* coords, double* means, double* covs, int32_t* num_points);
+/* GaussianVoxelMapCPU::save_compact / ::load (src/gtsam_points/types/gaussian_voxelmap_cpu.cpp:79-135): the reference's wire
+ * format -- 7 text header lines, then num_voxels packed 56-byte GaussianVoxelData records (types/gaussian_voxel_data.hpp:11-54:
+ * int32 coord[3], int32 num_points, float mean[3], float cov[6] = (00,01,02,11,12,22), float intensity).  Files written by either
+ * side load on the other. */
+B2_API b2_status b2_voxelmap_save_compact(const b2_voxelmap* vm, const char* path);
+B2_API b2_status b2_voxelmap_load(b2_ctx* ctx, const char* path, b2_voxelmap** out);
+/* overlap_gpu (include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:116-125, src/.../gaussian_voxelmap_gpu_funcs.cu:65-194):
+ * fraction of the source points p for which T_j p lies in a voxel of target j for some j (first match counts).
+ * Ts_target_source: num_targets x 16 doubles (row-major 4x4). */
+B2_API b2_status b2_overlap(const b2_voxelmap* const* targets, size_t num_targets, const b2_cloud* source, const double* Ts_target_source, double* out_overlap);
 /* voxel_coord + lookup_voxel_index for n host points (gaussian_voxelmap_cpu.cpp:59-69); out_index[i] = id or -1 */
 B2_API b2_status b2_voxelmap_lookup(const b2_voxelmap* vm, const double* points, int point_stride, size_t n, int32_t* out_index);
 
@@ -151,6 +177,20 @@ B2_API b2_status b2_kdtree_destroy(b2_kdtree* tree);
  * < max_sq_dist, else -1; out_sq_dist[i] = its squared distance (max_sq_dist if none).  Either output may be NULL. */
 B2_API b2_status b2_kdtree_knn1(const b2_kdtree* tree, const double* queries, int query_stride, size_t nq, double max_sq_dist, int64_t* out_index,
                                 double* out_sq_dist);
+
+/* General form: the k nearest neighbours, 1 <= k <= B2_KNN_MAX_K, of every query -- NearestNeighborSearch::knn_search with
+ * KnnResult's output convention (include/gtsam_points/ann/knn_result.hpp:44-109): out_index / out_sq_dist are nq x k, sorted by
+ * distance, entries beyond the number found hold (-1, max_sq_dist); exact (KnnSetting::epsilon = 0). */
+#define B2_KNN_MAX_K 64
+B2_API b2_status b2_kdtree_knn(const b2_kdtree* tree, const double* queries, int query_stride, size_t nq, int k, double max_sq_dist, int64_t* out_index,
+                               double* out_sq_dist);
+/* estimate_covariances (include/gtsam_points/features/covariance_estimation.hpp:14-66, src/.../covariance_estimation.cpp:18-77):
+ * per point the covariance of its k nearest neighbours (itself included), EIG-regularised: eigenvalues replaced by
+ * eigen_values[3] in ascending-eigenvalue order (NULL = the reference's default (1e-3, 1, 1)).  out_cov3x3: host, n x 9
+ * (row-major 3x3; embed into Matrix4d with zero row / column 3).  Points with fewer than k neighbours get identity.
+ * The first form builds its own kd-tree like the reference does; the second re-uses an existing tree over the same points. */
+B2_API b2_status b2_estimate_covariances(b2_ctx* ctx, const double* points, int point_stride, size_t n, int k_neighbors, const double* eigen_values, double* out_cov3x3);
+B2_API b2_status b2_kdtree_estimate_covariances(const b2_kdtree* tree, int k_neighbors, const double* eigen_values, double* out_cov3x3);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Factors.  Replace IntegratedVGICPFactor_ / IntegratedVGICPFactorGPU and IntegratedGICPFactor_
@@ -175,6 +215,13 @@ B2_API b2_status b2_factor_linearize(b2_factor* f, const double* delta, b2_linea
  * (integrated_matching_cost_factor.cpp:32-35, integrated_vgicp_factor_impl.hpp:183-224).  If the factor has never been
  * linearized, correspondences are first established at delta_eval (integrated_vgicp_factor_impl.hpp:183-185). */
 B2_API b2_status b2_factor_error(b2_factor* f, const double* delta_eval, double* out_error);
+
+/* Per-factor asynchronous protocol: the device half of NonlinearFactorGPU::issue_linearize / issue_compute_error / sync
+ * (include/gtsam_points/factors/nonlinear_factor_gpu.hpp:85-121).  delta is a HOST pose (captured before the call returns),
+ * d_out a DEVICE pointer (1 KiB record / one double); the kernel is enqueued on the factor's context stream. */
+B2_API b2_status b2_factor_issue_linearize(b2_factor* f, const double* delta, double* d_out);
+B2_API b2_status b2_factor_issue_error(b2_factor* f, const double* delta_eval, double* d_out_error);
+B2_API b2_status b2_factor_sync(b2_factor* f);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Factor sets.  Replace NonlinearFactorSetGPU::linearize / ::error

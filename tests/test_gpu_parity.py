@@ -271,8 +271,9 @@ def test_no_correspondence_and_error_reporting(g, scene):
         bad = sp.copy()
         bad[3, 1] = np.nan
         g.PointCloud(bad, sc)
-    with pytest.raises(RuntimeError):
-        vm.insert(g.PointCloud(tp, tc))  # incremental insertion is not supported on the GPU map
+    n_before = vm.num_voxels
+    vm.insert(g.PointCloud(tp, tc))  # a second insert() is incremental (CPU-map semantics): same voxels, doubled counts
+    assert vm.num_voxels == n_before
     empty = g.GaussianVoxelMapGPU(0.5)
     empty.insert(g.PointCloud(np.zeros((0, 3)), np.zeros((0, 3, 3))))
     assert empty.num_voxels == 0
@@ -317,3 +318,38 @@ def test_many_small_factors_exercise_run_boundaries(g, scene, oracle_map):
         eref = of.error(fs.factors[i].calc_delta(values))
         assert abs(errs[i] - eref) <= TOL * abs(eref) + 1e-300
     assert np.array_equal(out, fs.linearize(values))  # bit-reproducible
+
+
+def test_kdtree_ties_duplicate_points(g):
+    """Exact ties: duplicated target points (equal squared distances).  The reference keeps the candidate it visits FIRST
+    (strict '<', ann/knn_result.hpp:89-109), and which one that is depends on the shape of ITS tree (nth_element order inside
+    a leaf).  The device traversal visits leaves in another order, so among exactly equidistant points it may return another
+    index: what is guaranteed -- and tested -- is the same DISTANCE bit for bit, a returned point that attains it, and
+    identical H, b, error whenever the tied points also carry identical covariances (duplicates of the same point)."""
+    rng = np.random.default_rng(31)
+    base = np.round(rng.uniform(-20, 20, (4000, 3)), 2)
+    tp = np.concatenate([base, base[:1500], base[:700]])  # up to 3 copies of a point
+    perm = rng.permutation(len(tp))
+    tp = tp[perm]
+    cov1 = np.tile(np.diag([0.01, 0.02, 0.03]), (len(base), 1, 1)) + 0.001 * rng.uniform(0, 1, (len(base), 1, 1)) * np.eye(3)
+    tc = np.concatenate([cov1, cov1[:1500], cov1[:700]])[perm]  # copies share their covariance
+    q = np.concatenate([base[:3000] + rng.normal(0, 0.05, (3000, 3)), base[:500]])  # near and exactly on duplicated points
+    tree = g.KdTree(tp)
+    idx, sqd = tree.knn_search(q, 1, 4.0)
+    oidx, osqd, found = orc.KdTree(orc.Cloud(tp), num_threads=2).knn(q, 1, 4.0, num_threads=2)
+    assert np.array_equal(idx >= 0, found > 0)
+    v = idx >= 0
+    assert np.array_equal(sqd[v], osqd[v, 0])  # the same minimum, bit for bit
+    assert np.array_equal(((tp[idx[v]] - q[v]) ** 2).sum(1) <= sqd[v] * (1 + 1e-15) + 1e-300, np.ones(v.sum(), bool))
+    assert np.array_equal(tp[idx[v]], tp[oidx[v, 0]])  # possibly another copy, but the same coordinates
+    # GICP over the duplicated target: identical linearization although correspondence indices may name another copy
+    sc = np.tile(np.diag([0.02, 0.01, 0.03]), (len(q), 1, 1))
+    f = g.IntegratedGICPFactor(0, 1, g.PointCloud(tp, tc), g.PointCloud(q, sc))
+    otgt = orc.Cloud(tp, tc)
+    of = orc.Factor(otgt, orc.Cloud(q, sc), tree=orc.KdTree(otgt, 2), num_threads=2)
+    delta = syn.random_pose(np.random.default_rng(2), 0.01, 0.05)
+    f.linearize({0: np.eye(4), 1: delta})
+    ref = of.linearize(delta)
+    c, oc = f.correspondences(), of.correspondences()
+    assert np.array_equal(c >= 0, oc >= 0) and np.array_equal(tp[c[c >= 0]], tp[oc[oc >= 0]])
+    assert_linearized_close(f._last, ref)
