@@ -77,6 +77,7 @@ SIGNATURES = {
     "b2_gicp_factor_create": (C.c_int, [_vp, _vp, _vp, _vp, _pp]),
     "b2_factor_destroy": (C.c_int, [_vp]),
     "b2_factor_set_max_correspondence_distance": (C.c_int, [_vp, C.c_double]),
+    "b2_factor_set_correspondence_update_tolerance": (C.c_int, [_vp, C.c_double, C.c_double]),
     "b2_factor_num_points": (C.c_size_t, [_vp]),
     "b2_factor_correspondences": (C.c_int, [_vp, _lp]),
     "b2_factor_linearize": (C.c_int, [_vp, _dp, _dp]),
@@ -99,6 +100,13 @@ SIGNATURES = {
     "b2_factor_set_linearize_exchange": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),
     "b2_exchange_wait": (C.c_int, [_vp, _vp, C.c_int, C.c_uint]),
     "b2_exchange_signal": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint]),
+    "b2_exchange_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_size_t, _pp]),
+    "b2_exchange_destroy": (C.c_int, [_vp]),
+    "b2_exchange_export": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "b2_exchange_import": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ubyte)]),
+    "b2_exchange_enable_peer": (C.c_int, [_vp, C.c_int, _vp]),
+    "b2_exchange_linearize": (C.c_int, [_vp, _vp, _dp, C.c_size_t, C.c_uint]),
+    "b2_exchange_records": (_vp, [_vp, C.c_uint]),
     "b2_factor_set_launch_count": (C.c_uint64, [_vp]),
 }
 

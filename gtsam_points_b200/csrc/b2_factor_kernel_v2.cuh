@@ -1,33 +1,31 @@
-// b2_factor_kernel_v2.cuh -- the hot kernel, second form: warp-specialised, every global stream staged asynchronously.
-// Included by b2_factors.cu after the shared pieces (FactorDesc, accumulate arithmetic, warp_reduce32, epilogue).
+// b2_factor_kernel_v2.cuh -- the hot kernel, second form: warp-specialised, every operand of the float64 arithmetic staged
+// asynchronously into shared memory.  Included by b2_factors.cu after the shared pieces (FactorDesc, accumulate arithmetic,
+// warp_reduce32, epilogue).
 //
 // Round-1's kernel (b2_factor_kernel_ws.cuh, still used by the kd-tree path) was latency bound: 16 warps per SM, each a
 // long dependent chain with its global loads on the scoreboard (probe warps: 48 % long-scoreboard stalls on the streamed
-// coordinates and the bucket group; accumulate warps: 11 gathers in front of every batch).  This form takes every byte
-// that CAN be known ahead of time off the scoreboards:
-//   * the STREAMS (3 coordinate planes, 6 covariance planes, the frozen correspondences in error mode: 94 % of the bytes)
-//     arrive through the TMA unit: two dedicated PRODUCER warps (one lane each; one for the coordinate stream, one for the
-//     covariance stream) issue 1-D bulk copies (cp.async.bulk, one per plane and CTA tile of kTile = 512 points: 2-4 KB
-//     each) into multi-stage shared-memory rings, completion on `full` mbarriers (complete_tx::bytes); stages are handed
-//     back through `empty` mbarriers on which every probe warp arrives once.  The probe warps never compute a global
-//     address for the streams.  A coordinate stage is released as soon as the probe warps have read it; a covariance
-//     stage is RETAINED until the accumulate warps have consumed every hit of the tile (they read the covariance of a hit
-//     from the stage by its tile-local index -- hits travel through the rings as 32-byte items (R p, stage slot, target id)).
-//   * the GATHERED target records (80 B per hit) are fetched by the accumulate warp for batch k + 1 with cp.async
-//     (LDGSTS, 5 x 16 B per lane) into a private double buffer while it computes batch k: the float64 arithmetic reads
-//     nothing but shared memory.
-//   * the pose of single-factor launches is a by-value kernel parameter: DMUL / DFMA take it as constant-bank operands
-//     (no registers, no shared-memory reads), and the kernel never touches host memory on its way in.
-// What stays on a scoreboard is the bucket group of the hash probe (data dependent address), 2 points per lane in flight.
+// coordinates and the bucket group; accumulate warps: 11 gathers in front of every batch).  Here
+//   * the coordinate STREAM (3 planes, + the frozen correspondences in error mode) arrives through the TMA unit: a dedicated
+//     PRODUCER warp (one lane) issues 1-D bulk copies (cp.async.bulk, one per plane and CTA tile of kTile = 512 points,
+//     2-4 KB each) into a multi-stage shared-memory ring, completion on `full` mbarriers (complete_tx::bytes); stages come
+//     back through `empty` mbarriers on which every probe warp arrives once.  The probe warps compute no stream address.
+//   * everything the arithmetic GATHERS per hit -- the target record (80 B) and the source covariance (6 values) -- is
+//     requested by the PROBE warp the moment it knows the hit, with cp.async (LDGSTS: no register, no scoreboard), straight
+//     into the hit's slot of the shared-memory ring, next to (R p, target id).  A tile's hits are published to the accumulate
+//     warp one tile later, when cp.async.wait_group says their operands have landed.  Misses are never fetched.
+//   * the ACCUMULATE warps therefore read nothing but shared memory: ten conflict-free LDS.128 per hit, then ~150 float64
+//     operations; no global access, no polling of memory latency.
+//   * the pose of single-factor launches is a by-value kernel parameter: DMUL / DFMA take it from uniform registers, and the
+//     kernel never touches host memory on its way in.
+// What stays on a scoreboard is the bucket group of the hash probe (data-dependent address), kPPL points per lane in flight.
 //
-// Stage retention and liveness.  A probe warp releases its share of a covariance stage only after its accumulate warp's
-// published `head` has passed the last hit of the tile that used it (`tile_end`).  Because the accumulate warp takes batches of exactly 32
-// consecutive hits, it could be waiting for hits that the probe warp cannot produce before the stage is free; in that case
-// (decided from hit counts alone, hence deterministic) the probe warp publishes a FORCED batch boundary `flush` = its
-// current tail: the accumulate warp then takes the shorter batch [head, flush).  Batch boundaries therefore depend only on
-// the data, never on timing: results stay bit-reproducible run to run.
-// Everything else (ring protocol, done / ack hand-shake per factor run, strict rotation, slot-ordered cross-CTA sums) is
-// the round-1 protocol.
+// Ring protocol (one ring per probe warp, single producer / single consumer, monotonic 32-bit counters in shared memory):
+// `tail` (published with st.release after the operands of those items have landed), `head` (released by the accumulate warp
+// after it has read a batch), `done` / `ack` (factor-run hand-shake: batches never straddle factors).  The accumulate warp
+// takes batches of exactly 32 consecutive hits (the last batch of a run may be shorter), rings are drained in strict
+// rotation, cross-warp / cross-CTA sums run in slot order: results are bit-reproducible run to run.
+// Liveness: a probe warp that has to wait for ring space first publishes everything it has in flight; ring capacity >=
+// one batch + one warp tile then guarantees that either side can always move.  All waits are bounded (trap, never hang).
 //
 // This file is included once per kernel configuration (no include guard); the includer defines B2_V2_NAMESPACE and the
 // B2_V2_* parameters (see b2_factors.cu).
@@ -44,20 +42,24 @@ constexpr int kWarpPoints = 32 * kPPL;   // contiguous source points per probe w
 constexpr int kTile = kP * kWarpPoints;  // source points per CTA tile
 constexpr int kRing = B2_V2_RING;        // items per ring (power of two)
 constexpr int kSX = B2_V2_XYZ_STAGES;    // coordinate stages (CTA tiles in flight ahead of the probe warps)
-constexpr int kSC = B2_V2_COV_STAGES;    // covariance stages
-constexpr int kRet = B2_V2_COV_RETAIN;   // a probe warp releases the covariance stage of tile j when it starts tile j + kRet: lookahead kSC - kRet tiles
+constexpr int kFields = 10;              // 16-byte fields per ring item: (u0,u1) (u2,slot|id) | record 5 x | covariance 3 x
 constexpr int kRingsPerConsumer = kP / kC;
 constexpr uint32_t kBatch = 32u;
 static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
 static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
-static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 + kWarpPoints, "ring capacity: a tile's hits + a batch being read + a batch");
-static_assert(kSX >= 2 && kRet >= 1 && kSC > kRet, "stage counts");
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 32 + kWarpPoints, "ring capacity: a batch the accumulate warp can take + a tile's hits");
+static_assert(kSX >= 2, "stage counts");
 // setmaxnreg moves registers inside the CTA's OWN pool (what the launch allocated: threads x the per-thread count the
 // launch bounds give); the SM's unallocated remainder is not available.  A split that asks for more deadlocks the
 // accumulate warps in USETMAXREG.TRY_ALLOC.
 constexpr int kLaunchRegs = ((65536 / kThreads) / 8) * 8 > 255 ? 248 : ((65536 / kThreads) / 8) * 8;
 static_assert(kP * B2_V2_REGS_PRODUCER + kC * B2_V2_REGS_CONSUMER + kAux * B2_V2_REGS_AUX <= (kP + kC + kAux) * kLaunchRegs, "register split exceeds the CTA's pool");
-static_assert(B2_V2_REGS_PRODUCER <= kLaunchRegs && B2_V2_REGS_AUX <= kLaunchRegs && B2_V2_REGS_CONSUMER >= kLaunchRegs, "dec / inc directions");
+// per-role register count relative to what the launch handed every thread: release, keep, or (blocking until released) acquire
+template <int REGS>
+__device__ __forceinline__ void set_role_registers() {
+  if constexpr (REGS < kLaunchRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+  if constexpr (REGS > kLaunchRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
 
 constexpr unsigned kSpinLimit = 1u << 25;  // polls (with sleeps: >= 2 s) before a wait traps: a protocol bug must not hang the GPU
 
@@ -119,6 +121,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(uint32_t dst, const void* src) {  // 4 or 8 bytes
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -126,29 +132,21 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ---- shared-memory layout ---------------------------------------------------------------------------------------------
-// dynamic part: [kSX coordinate stages | kSC covariance stages] (CTA tiles), then one ring per probe warp, then per accumulate
-// warp the record double buffer.  Everything is a multiple of 128 bytes.
-constexpr uint32_t kRecBufBytes = 32u * kRecordDoubles * 8u;  // one batch of gathered target records
+// dynamic part: [kSX coordinate stages] (CTA tiles), then one ring per probe warp.  Everything is a multiple of 128 bytes.
 template <typename PT, int MODE>
 struct XyzStage {
   static constexpr uint32_t kPlane = kTile * sizeof(PT);
   static constexpr uint32_t kCorrOff = 3u * kPlane;
   static constexpr uint32_t kBytes = 3u * kPlane + (MODE == MODE_ERROR ? kTile * 4u : 0u);
 };
-template <typename CT>
-struct CovStage {
-  static constexpr uint32_t kPlane = kTile * sizeof(CT);
-  static constexpr uint32_t kBytes = 6u * kPlane;
-};
-constexpr uint32_t kRingBytes1 = 2u * kRing * 16u;
+constexpr uint32_t kFieldBytes = kRing * 16u;              // one field of every slot (structure of arrays: lane -> slot is conflict-free)
+constexpr uint32_t kRingBytes1 = kFields * kFieldBytes;    // 160 bytes per item
 template <typename PT, typename CT, int MODE>
 struct Layout {
   static constexpr uint32_t kXyzOff = 0u;
-  static constexpr uint32_t kCovOff = kSX * XyzStage<PT, MODE>::kBytes;
-  static constexpr uint32_t kRingOff = kCovOff + kSC * CovStage<CT>::kBytes;
-  static constexpr uint32_t kRecOff = kRingOff + kP * kRingBytes1;
-  static constexpr uint32_t kTotal = kRecOff + kC * 2u * kRecBufBytes;
-  static_assert(kCovOff % 128u == 0u && kRingOff % 128u == 0u, "stage alignment");
+  static constexpr uint32_t kRingOff = kSX * XyzStage<PT, MODE>::kBytes;
+  static constexpr uint32_t kTotal = kRingOff + kP * kRingBytes1;
+  static_assert(kRingOff % 128u == 0u, "stage alignment");
 };
 
 struct Shared {
@@ -164,13 +162,9 @@ struct Shared {
   uint32_t head[kP];   // items consumed (operands read) by the accumulate warp
   uint32_t done[kP];   // factor runs completed by the probe warp (tail is final for run e once done == e + 1)
   uint32_t ack[kP];    // factor runs the accumulate warp has finished draining
-  uint32_t flush[kP];  // forced batch boundary (a tail value): the accumulate warp may take the short batch [head, flush)
-  uint32_t tile_end[kP][kSC];  // tail after the tile that last used covariance stage s
   double probe_pose[kP][12];   // per probe warp: R (9, row-major) | t (3) of the factor run it is working on (multi-factor launches)
   alignas(8) uint64_t full_x[kSX];   // coordinate stage s has landed (1 arrival + tx bytes)
   alignas(8) uint64_t empty_x[kSX];  // every probe warp is done reading it (kP arrivals)
-  alignas(8) uint64_t full_c[kSC];   // covariance stage s has landed
-  alignas(8) uint64_t empty_c[kSC];  // every probe warp's accumulate warp has consumed the tile's hits (kP arrivals)
 };
 
 // tiles of CTA c: [c * T / G, (c + 1) * T / G) -- contiguous and balanced; the host uses the same formula for the slots
@@ -281,10 +275,9 @@ template <typename PT, typename CT, int KIND, int MODE, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 1)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
               const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-              const __grid_constant__ DoneSignal sig, const __grid_constant__ PoseArg pose) {
+              const __grid_constant__ DoneSignal sig, const __grid_constant__ PoseArg pose, const uint32_t* __restrict__ /*frozen_flags: kd-tree factors only*/) {
   using L = Layout<PT, CT, MODE>;
   using XS = XyzStage<PT, MODE>;
-  using CS = CovStage<CT>;
   __shared__ Shared sh;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
 
@@ -294,20 +287,12 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     sh.head[tid] = 0u;
     sh.done[tid] = 0u;
     sh.ack[tid] = 0u;
-    sh.flush[tid] = 0u;
-#pragma unroll
-    for (int s = 0; s < kSC; s++) sh.tile_end[tid][s] = 0u;
   }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kSX; s++) {
       mbar_init(&sh.full_x[s], 1u);
       mbar_init(&sh.empty_x[s], kP);
-    }
-#pragma unroll
-    for (int s = 0; s < kSC; s++) {
-      mbar_init(&sh.full_c[s], 1u);
-      mbar_init(&sh.empty_c[s], kP);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -318,13 +303,38 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
   const uint32_t tile_hi = cta_tile_begin(blockIdx.x + 1, num_tiles, G);
 
   if (warp >= kP + kC) {
-    // ================================================ PRODUCER warps ================================================
-    // aux warp 0 streams the coordinate planes (+ frozen correspondences), aux warp 1 the covariance planes: one lane each,
-    // running ahead of the probe warps as far as the stages allow -- across factor boundaries, too.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_AUX));
-    const int role = warp - (kP + kC);
-    if (role > 1 || lane != 0) return;
-    uint32_t j = 0u;  // CTA tiles issued so far: stage = j % S, use count = j / S
+    // ================================================= PRODUCER warp =================================================
+    // aux warp 0, one lane: streams the coordinate planes (+ frozen correspondences) of the CTA's tiles, running ahead of the
+    // probe warps as far as the stages allow -- across factor boundaries, too.  (setmaxnreg works on warpgroups: the other
+    // three warps of this group only give their registers back.)
+    set_role_registers<B2_V2_REGS_AUX>();
+#if B2_V2_WARM_L2
+    if (warp != kP + kC) {
+      // The other three warps of this group stream the GATHERED arrays of the CTA's first factor -- bucket table and target
+      // records, a few MB that every point probes at random -- into L2, each CTA its share, with coalesced prefetches: the
+      // random first touches of the probe / operand gathers then find L2 lines instead of paying a DRAM round trip each.
+      const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile_lo));
+      const uint32_t share = dg->num_slots[MODE], me = blockIdx.x - dg->cta_first[MODE];
+      const int w = warp - (kP + kC) - 1;  // 0..2
+      auto warm = [&](const char* ptr, size_t bytes) {
+        const size_t lines = (bytes + 127) / 128;
+        const size_t per = (lines + share - 1) / share;
+        const size_t lo = static_cast<size_t>(me) * per, hi = min(lines, lo + per);
+        for (size_t l = lo + static_cast<size_t>(w) * 32 + lane; l < hi; l += 96) prefetch_l2(ptr + l * 128);
+      };
+      if (me < share) {
+        if (KIND == 0) warm(reinterpret_cast<const char*>(dg->buckets), (static_cast<size_t>(dg->bucket_mask) + 1) * kGroup * sizeof(VoxelBucket));
+#if B2_V2_WARM_L2 > 1
+        if (KIND == 0) warm(reinterpret_cast<const char*>(dg->records), static_cast<size_t>(dg->num_records) * kRecordDoubles * sizeof(double));
+#endif
+      }
+      return;
+    }
+    if (lane != 0) return;
+#else
+    if (warp != kP + kC || lane != 0) return;
+#endif
+    uint32_t j = 0u;  // CTA tiles issued so far: stage = j % kSX, use count = j / kSX
     uint32_t tile = tile_lo;
 #ifdef B2_V2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -336,39 +346,25 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const uint32_t f_tile_begin = dg->tile_begin, f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
       const uint32_t run_end = min(tile_hi, f_tile_begin + f_num_tiles);
       const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
-      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
       const int32_t* __restrict__ corr = dg->corr;
       uint32_t pt = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles);
       for (; tile < run_end; tile++, j++) {
         const uint32_t base = pt * kTile;
         const uint32_t cnt = base >= n_pad ? 0u : min(static_cast<uint32_t>(kTile), n_pad - base);  // multiple of 32
-        if (role == 0) {
-          const uint32_t s = j % kSX;
+        const uint32_t s = j % kSX;
+        {
           B2_T0(tw);
           if (j >= static_cast<uint32_t>(kSX)) mbar_wait(&sh.empty_x[s], ((j / kSX) - 1u) & 1u);
           B2_TACC(0, tw);
-          fence_proxy_async();  // the stage was read through the generic proxy
-          const uint32_t dst = smem_u32(dyn_smem + L::kXyzOff + s * XS::kBytes);
-          mbar_expect_tx(&sh.full_x[s], cnt * (3u * static_cast<uint32_t>(sizeof(PT)) + (MODE == MODE_ERROR ? 4u : 0u)));
-          if (cnt) {
-            const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(PT));
+        }
+        fence_proxy_async();  // the stage was read through the generic proxy
+        const uint32_t dst = smem_u32(dyn_smem + L::kXyzOff + s * XS::kBytes);
+        mbar_expect_tx(&sh.full_x[s], cnt * (3u * static_cast<uint32_t>(sizeof(PT)) + (MODE == MODE_ERROR ? 4u : 0u)));
+        if (cnt) {
+          const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(PT));
 #pragma unroll
-            for (int a = 0; a < 3; a++) bulk_g2s(dst + a * XS::kPlane, px + static_cast<size_t>(a) * n_pad + base, bytes, &sh.full_x[s]);
-            if (MODE == MODE_ERROR) bulk_g2s(dst + XS::kCorrOff, corr + base, cnt * 4u, &sh.full_x[s]);
-          }
-        } else {
-          const uint32_t s = j % kSC;
-          B2_T0(tw);
-          if (j >= static_cast<uint32_t>(kSC)) mbar_wait(&sh.empty_c[s], ((j / kSC) - 1u) & 1u);
-          B2_TACC(0, tw);
-          fence_proxy_async();
-          const uint32_t dst = smem_u32(dyn_smem + L::kCovOff + s * CS::kBytes);
-          mbar_expect_tx(&sh.full_c[s], cnt * 6u * static_cast<uint32_t>(sizeof(CT)));
-          if (cnt) {
-            const uint32_t bytes = cnt * static_cast<uint32_t>(sizeof(CT));
-#pragma unroll
-            for (int a = 0; a < 6; a++) bulk_g2s(dst + a * CS::kPlane, cv + static_cast<size_t>(a) * n_pad + base, bytes, &sh.full_c[s]);
-          }
+          for (int a = 0; a < 3; a++) bulk_g2s(dst + a * XS::kPlane, px + static_cast<size_t>(a) * n_pad + base, bytes, &sh.full_x[s]);
+          if (MODE == MODE_ERROR) bulk_g2s(dst + XS::kCorrOff, corr + base, cnt * 4u, &sh.full_x[s]);
         }
         pt += perm_stride;
         if (pt >= f_num_tiles) pt -= f_num_tiles;
@@ -383,12 +379,15 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 
   if (warp < kP) {
     // ================================================= PROBE warps =================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_PRODUCER));
+    set_role_registers<B2_V2_REGS_PRODUCER>();
     const int p = warp;
+    const uint32_t ring_s = smem_u32(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
     double2* const ring = reinterpret_cast<double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
-    uint32_t tail = 0u, run = 0u;
-    uint32_t j = 0u;    // CTA tiles this warp has processed so far (all runs): stage = j % S, use count = j / S
-    uint32_t rel = 0u;  // CTA tiles whose covariance stage this warp has released
+    uint32_t tail = 0u;       // items written (operands requested)
+    uint32_t committed = 0u;  // tail at the previous tile's cp.async commit: those items' operands are the next to land
+    uint32_t published = 0u;  // tail the accumulate warp has been told about
+    uint32_t run = 0u;
+    uint32_t j = 0u;  // CTA tiles this warp has processed so far (all runs): stage = j % kSX, use count = j / kSX
     uint32_t head_seen = 0u;
     uint32_t tile = tile_lo;
 #ifdef B2_V2_TIMING
@@ -398,9 +397,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     while (tile < tile_hi) {
       const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
       const uint32_t n = dg->n;
+      const size_t n_pad = dg->n_pad;
       const uint32_t f_tile_begin = dg->tile_begin;
       const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
       const uint32_t out_index = dg->out_index;
+      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
       const double* __restrict__ records = dg->records;
       int32_t* __restrict__ corr = dg->corr;
       const VoxelBucket* __restrict__ buckets = dg->buckets;
@@ -414,7 +415,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         }
         __syncwarp();
       }
-      // pose the correspondences are searched at: constant-bank operands (SINGLE) or this warp's shared-memory slot
+      // pose the correspondences are searched at: uniform-register operands (SINGLE) or this warp's shared-memory slot
       auto Rm = [&](int i) -> double { return SINGLE ? pose.m[(i / 3) * 4 + (i % 3)] : sh.probe_pose[p][i]; };
       auto tv = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : sh.probe_pose[p][9 + i]; };
       const KdTreeView tview{dg->nodes, dg->leaf_pts, static_cast<int>(dg->leaf_f32)};
@@ -424,110 +425,123 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       // S ~ 0.618 n_tiles coprime to n_tiles: every CTA samples the (Morton-ordered) cloud quasi-uniformly.
       const uint32_t f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
       uint32_t pt_cur = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles);
-      uint32_t grid_base = tail;  // the accumulate warp's batches of this run start at grid_base + 32 i (until a forced boundary)
 
-      // this warp's share of covariance stage (r % kSC) goes back to the producer once the accumulate warp has consumed the
-      // last hit of tile r (`head` >= tile_end); forces a batch boundary if the accumulate warp could not get there otherwise
-      auto release_tile = [&](uint32_t r) {
-        const uint32_t s = r % kSC;
-        const uint32_t e = sh.tile_end[p][s];
-        if (static_cast<int32_t>(head_seen - e) < 0) {
-          head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
-          if (static_cast<int32_t>(head_seen - e) < 0) {
-            // can the accumulate warp get there with full batches?  (deterministic: depends on hit counts only)
-            const uint32_t need = grid_base + ((e - grid_base + 31u) & ~31u);
-            if (static_cast<int32_t>(tail - need) < 0) {
-              if (lane == 0) st_release(&sh.flush[p], tail);  // forced batch boundary at the current tail
-              grid_base = tail;
-            }
-            Backoff bo(32u, 256u);
-            do {
-              bo.wait();
-              head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
-            } while (static_cast<int32_t>(head_seen - e) < 0);
-          }
-        }
-        if (lane == 0) mbar_arrive(&sh.empty_c[s]);
-      };
-
-#pragma unroll 1
-      for (; tile < run_end; tile++, j++) {
-        {
-          B2_T0(tw);
-          if (j - rel >= static_cast<uint32_t>(kRet)) release_tile(rel++);
-          B2_TACC(0, tw);
-        }
-
-        // ---- this tile's coordinates ----
-        const uint32_t sx = j % kSX;
-        {
-          B2_T0(tw);
-          mbar_wait(&sh.full_x[sx], (j / kSX) & 1u);
-          B2_TACC(1, tw);
-        }
-        B2_T0(t_work);
-        const unsigned char* xs = dyn_smem + L::kXyzOff + sx * XS::kBytes;
-        const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
+      // Per tile, two phases, software-pipelined one tile apart:
+      //   A(j + 1): read the tile's coordinates from the stage, rotate, floor, hash, start the bucket group of every point
+      //             towards L2 (prefetch: no register, no scoreboard), hand the stage back -- results stay in registers;
+      //   B(j):     load the (now L2-resident) bucket groups, match, store corr[], compact the hits into the ring and request
+      //             their operands.
+      struct Pre {
         double u[kPPL][3];
         int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
         uint32_t grp_idx[kPPL];
         bool ok[kPPL];
-        BucketGroup grp[kPPL];
+      };
+      auto phase_a = [&](Pre& a, uint32_t jj, uint32_t pt) {
+        const uint32_t sx = jj % kSX;
+        {
+          B2_T0(tw);
+          mbar_wait(&sh.full_x[sx], (jj / kSX) & 1u);
+          B2_TACC(1, tw);
+        }
+        const unsigned char* xs = dyn_smem + L::kXyzOff + sx * XS::kBytes;
+        const uint32_t base = pt * kTile + p * kWarpPoints + lane;
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
           const int li = p * kWarpPoints + lane + 32 * q;
-          ok[q] = base + 32 * q < n;
+          a.ok[q] = base + 32 * q < n;
           const double x = static_cast<double>(reinterpret_cast<const PT*>(xs)[li]);
           const double y = static_cast<double>(reinterpret_cast<const PT*>(xs + XS::kPlane)[li]);
           const double z = static_cast<double>(reinterpret_cast<const PT*>(xs + 2 * XS::kPlane)[li]);
-          id[q] = -1;
-          if (MODE == MODE_ERROR) id[q] = ok[q] ? reinterpret_cast<const int*>(xs + XS::kCorrOff)[li] : -1;
+          a.id[q] = -1;
+          if (MODE == MODE_ERROR) a.id[q] = a.ok[q] ? reinterpret_cast<const int*>(xs + XS::kCorrOff)[li] : -1;
           // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
-          u[q][0] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
-          u[q][1] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
-          u[q][2] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
+          a.u[q][0] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
+          a.u[q][1] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
+          a.u[q][2] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
+          a.cx[q] = a.cy[q] = a.cz[q] = 0;
+          a.grp_idx[q] = 0u;
           if (MODE == MODE_LINEARIZE && KIND == 0) {
-            cx[q] = voxel_coord1(__dadd_rn(u[q][0], tv(0)), inv_leaf);
-            cy[q] = voxel_coord1(__dadd_rn(u[q][1], tv(1)), inv_leaf);
-            cz[q] = voxel_coord1(__dadd_rn(u[q][2], tv(2)), inv_leaf);
-            grp_idx[q] = voxel_hash(cx[q], cy[q], cz[q]) & bucket_mask;
-#ifndef B2_V2_DEBUG_NO_PROBE
-            grp[q] = load_group(buckets, grp_idx[q]);
+            a.cx[q] = voxel_coord1(__dadd_rn(a.u[q][0], tv(0)), inv_leaf);
+            a.cy[q] = voxel_coord1(__dadd_rn(a.u[q][1], tv(1)), inv_leaf);
+            a.cz[q] = voxel_coord1(__dadd_rn(a.u[q][2], tv(2)), inv_leaf);
+            a.grp_idx[q] = voxel_hash(a.cx[q], a.cy[q], a.cz[q]) & bucket_mask;
+#if B2_V2_PREFETCH_GROUPS
+            const char* gp = reinterpret_cast<const char*>(buckets) + static_cast<size_t>(a.grp_idx[q]) * (kGroup * sizeof(VoxelBucket));
+            prefetch_l2(gp);
+            prefetch_l2(gp + 32);
 #endif
           }
         }
         // every lane has read its coordinates: the stage goes back to the producer (one arrival per probe warp)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_x[sx]);
+      };
+
+      Pre cur;
+#if B2_V2_PIPELINE_A
+      Pre nxt;
+      phase_a(nxt, j, pt_cur);
+#endif
+#pragma unroll 1
+      for (; tile < run_end; tile++, j++) {
+        B2_T0(t_work);
+#if B2_V2_PIPELINE_A
+        cur = nxt;
+#else
+        phase_a(cur, j, pt_cur);
+#endif
+        const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
+        int id[kPPL];
+        BucketGroup grp[kPPL];
+#pragma unroll
+        for (int q = 0; q < kPPL; q++) {
+          id[q] = cur.id[q];
+#ifndef B2_V2_DEBUG_NO_PROBE
+          if (MODE == MODE_LINEARIZE && KIND == 0) grp[q] = load_group(buckets, cur.grp_idx[q]);
+#endif
+        }
+        pt_cur += perm_stride;
+        if (pt_cur >= f_num_tiles) pt_cur -= f_num_tiles;
+#if B2_V2_PIPELINE_A
+        if (tile + 1 < run_end) phase_a(nxt, j + 1, pt_cur);  // overlaps the bucket-group loads above
+#endif
         uint32_t mask[kPPL], cnt = 0u;
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
           if (MODE == MODE_LINEARIZE) {
             if (KIND == 0) {
 #ifdef B2_V2_DEBUG_NO_PROBE
-              id[q] = static_cast<int>(grp_idx[q] & 0xffffu);  // measurement aid: no table access, every point "hits" some record
+              id[q] = static_cast<int>(cur.grp_idx[q] & 0xffffu);  // measurement aid: no table access, every point "hits" some record
 #else
-              id[q] = match_group(grp[q], cx[q], cy[q], cz[q]);
+              id[q] = match_group(grp[q], cur.cx[q], cur.cy[q], cur.cz[q]);
 #endif
-              uint32_t g = grp_idx[q];
+              uint32_t g = cur.grp_idx[q];
               while (id[q] == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
                 g = (g + 1) & bucket_mask;
-                id[q] = match_group(load_group(buckets, g), cx[q], cy[q], cz[q]);
+                id[q] = match_group(load_group(buckets, g), cur.cx[q], cur.cy[q], cur.cz[q]);
               }
             } else {
               double sq;
-              id[q] = kdtree_nn1_warp(tview, __dadd_rn(u[q][0], tv(0)), __dadd_rn(u[q][1], tv(1)), __dadd_rn(u[q][2], tv(2)), ok[q], max_sq, &sq);
+              id[q] = kdtree_nn1_warp(tview, __dadd_rn(cur.u[q][0], tv(0)), __dadd_rn(cur.u[q][1], tv(1)), __dadd_rn(cur.u[q][2], tv(2)), cur.ok[q], max_sq, &sq);
             }
-            if (ok[q]) corr[base + 32 * q] = id[q];
+            if (cur.ok[q]) corr[base + 32 * q] = id[q];
           }
-          mask[q] = __ballot_sync(0xffffffffu, ok[q] && id[q] >= 0);
+          mask[q] = __ballot_sync(0xffffffffu, cur.ok[q] && id[q] >= 0);
           cnt += __popc(mask[q]);
         }
-        const uint32_t sc = j % kSC;
         B2_TACC(2, t_work);
         B2_T0(t_ring);
+        // The PREVIOUS tile's operands were requested a whole tile ago: wait for them and publish its hits -- BEFORE this
+        // tile's requests are issued, so that the release fence below has no copy of its own in flight to wait for.
+        cp_async_wait<0>();
+        if (committed != published) {
+          __syncwarp();
+          if (lane == 0) st_release(&sh.tail[p], committed);
+          published = committed;
+        }
         if (cnt != 0u) {
-          // room in the ring
+          // room in the ring (everything written so far is published: the accumulate warp can always move)
           if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
             head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
             if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
@@ -542,38 +556,36 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           for (int q = 0; q < kPPL; q++) {
             if ((mask[q] >> lane) & 1u) {
               const uint32_t slot = (tail + __popc(mask[q] & ((1u << lane) - 1u))) & (kRing - 1);
-              const uint32_t loc = sc * kTile + p * kWarpPoints + lane + 32 * q;  // where the accumulate warp finds this point's covariance
-              const unsigned long long bits = static_cast<unsigned long long>(loc) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
-              ring[slot] = make_double2(u[q][0], u[q][1]);
-              ring[kRing + slot] = make_double2(u[q][2], __longlong_as_double(static_cast<long long>(bits)));
-#if B2_V2_PREFETCH_RECORDS
+              const unsigned long long bits = static_cast<unsigned long long>(slot) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
+              ring[slot] = make_double2(cur.u[q][0], cur.u[q][1]);
+              ring[kRing + slot] = make_double2(cur.u[q][2], __longlong_as_double(static_cast<long long>(bits)));
+              // operands of this hit, requested now, landed before the hit is published: target record (5 x 16 B) ...
               const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(id[q]) * kRecordDoubles);
-              prefetch_l2(rec);
-              prefetch_l2(rec + 72);
-#endif
+              const uint32_t dst = ring_s + 2u * kFieldBytes + slot * 16u;
+#pragma unroll
+              for (int k = 0; k < 5; k++) cp_async16(dst + k * kFieldBytes, rec + 16 * k);
+              // ... and the source covariance (6 planes): (a00, a01) (a02, a11) (a12, a22), one 8-byte cell each
+              const CT* cp = cv + (base + 32 * q);
+              const uint32_t dc = ring_s + 7u * kFieldBytes + slot * 16u;
+#pragma unroll
+              for (int k = 0; k < 6; k++) cp_async_small<static_cast<int>(sizeof(CT))>(dc + (k >> 1) * kFieldBytes + (k & 1) * 8u, cp + static_cast<size_t>(k) * n_pad);
             }
             tail += __popc(mask[q]);
           }
         }
+        cp_async_commit();
+        committed = tail;
         B2_TACC(3, t_ring);
-        // the tile's covariances must have landed before its hits become visible to the accumulate warp
-        {
-          B2_T0(tw);
-          mbar_wait(&sh.full_c[sc], (j / kSC) & 1u);
-          B2_TACC(4, tw);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          sh.tile_end[p][sc] = tail;
-          st_release(&sh.tail[p], tail);
-        }
-        pt_cur += perm_stride;
-        if (pt_cur >= f_num_tiles) pt_cur -= f_num_tiles;
       }
-      // end of this CTA's run of the factor: publish, then wait until the accumulate warp has drained the ring
+      // end of this CTA's run of the factor: everything lands, is published, then wait until the accumulate warp has drained the ring
+      cp_async_wait<0>();
       run++;
       __syncwarp();
-      if (lane == 0) st_release(&sh.done[p], run);
+      if (lane == 0) {
+        st_release(&sh.tail[p], tail);
+        st_release(&sh.done[p], run);
+      }
+      committed = published = tail;
       {
         B2_T0(tw);
         Backoff bo(128u, 512u);
@@ -582,25 +594,23 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       }
       head_seen = tail;
       __syncwarp();
-      // everything published so far has been consumed: hand the outstanding covariance stages back
-      while (rel < j) {
-        if (lane == 0) mbar_arrive(&sh.empty_c[rel % kSC]);
-        rel++;
-      }
     }
 #ifdef B2_V2_TIMING
     tacc[7] = clock64() - t_begin;
+    {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      tacc[6] = smid;
+    }
     if (lane == 0)
       for (int k = 0; k < 8; k++) g_warp_cycles[(blockIdx.x * 32 + warp) * 8 + k] = tacc[k];
 #endif
   } else {
     // =============================================== ACCUMULATE warps ===============================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_V2_REGS_CONSUMER));
+    set_role_registers<B2_V2_REGS_CONSUMER>();
     const int cw = warp - kP;        // accumulate warp index
     const int ctid = tid - kP * 32;  // thread index within the accumulate group
-    unsigned char* const recbuf = dyn_smem + L::kRecOff + static_cast<size_t>(cw) * 2u * kRecBufBytes;
-    const unsigned char* const cov_stages = dyn_smem + L::kCovOff;
-    uint32_t head[kRingsPerConsumer];  // items taken (fetched) from each of this warp's rings
+    uint32_t head[kRingsPerConsumer];  // items taken from each of this warp's rings
 #pragma unroll
     for (int r = 0; r < kRingsPerConsumer; r++) head[r] = 0u;
     uint32_t run = 0u;
@@ -627,7 +637,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           sh.RL[ctid - 12] = pl[((ctid - 12) / 3) * 4 + (ctid - 12) % 3];
       }
       consumer_barrier();
-      // pose operands of the arithmetic: constant bank where the launch allows it, else registers
+      // pose operands of the arithmetic: uniform registers where the launch allows it, else registers
       constexpr bool kConstRL = SINGLE && MODE == MODE_LINEARIZE;
       double RLr[kConstRL ? 1 : 9], tr[SINGLE ? 1 : 3];
       if (!kConstRL) {
@@ -642,24 +652,16 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       auto tt = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : tr[SINGLE ? 0 : i]; };
 #pragma unroll
       for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
-      const double* __restrict__ records = d.records;
       const uint32_t run_end = min(tile_hi, d.tile_begin + d.num_tiles);
       run++;
 
-      // One batch = up to 32 consecutive hits of one ring.  `cur` is being computed, `nxt` has been fetched (its target
-      // records are on their way into the other half of the record buffer).
-      struct Bat {
-        uint32_t hd, nb;
-        int r;
-        bool fin, valid;
-      };
+      // Strict rotation over this warp's rings, in batches of 32 consecutive items (always full except for a probe warp's
+      // last batch of the run).  Every operand is in the ring item: ten 16-byte fields, lane -> slot, conflict-free.
       constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
-      uint32_t finished = 0u;  // rings whose final batch of this run has been FETCHED
-      int rot = 0;             // next ring in the strict rotation
-      uint32_t buf = 0u;
-
-      // take the next batch of ring r if it is there (blocking: wait for it); on success the records are requested
-      auto fetch = [&](int r, bool blocking, Bat& b, uint32_t which) -> bool {
+      uint32_t finished = 0u;
+      int r = 0;
+      while (finished != kAllFinished) {
+        while (finished & (1u << r)) r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
         const int p = cw + r * kC;
         uint32_t hd = 0u;
 #pragma unroll
@@ -667,129 +669,69 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           if (k == r) hd = head[k];
         uint32_t nb = 0u;
         bool fin = false;
-        Backoff bo(32u, 128u);
-        while (true) {
-          const uint32_t dn = ld_acquire(&sh.done[p]);
-          const uint32_t fl = ld_acquire(&sh.flush[p]);
-          const uint32_t tl = ld_acquire(&sh.tail[p]);
-          const uint32_t avail = tl - hd;
-          if (avail >= kBatch) {
-            nb = kBatch;
-            break;
-          }
-          if (static_cast<int32_t>(fl - hd) > 0) {  // forced boundary: the probe warp waits for this short batch
-            nb = fl - hd;
-            break;
-          }
-          if (dn == run) {  // the probe warp finished this run: `tl` is final
-            nb = avail;
-            fin = true;
-            break;
-          }
-          if (!blocking) return false;
-          bo.wait();
-        }
-        b.hd = hd;
-        b.nb = nb;
-        b.r = r;
-        b.fin = fin;
-        b.valid = true;
-#pragma unroll
-        for (int k = 0; k < kRingsPerConsumer; k++)
-          if (k == r) head[k] = hd + nb;
-        if (fin) finished |= 1u << r;
-        // request the target records of the batch: 5 x 16 B per hit, straight into shared memory (no registers, no scoreboard)
-        if (static_cast<uint32_t>(lane) < nb) {
-          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
-          const uint32_t slot = (hd + lane) & (kRing - 1);
-          const int id = static_cast<int>(static_cast<unsigned long long>(__double_as_longlong(rg[kRing + slot].y)) >> 32);
-          const char* src = reinterpret_cast<const char*>(records + static_cast<size_t>(id) * kRecordDoubles);
-          const uint32_t dst = smem_u32(recbuf + which * kRecBufBytes + lane * (kRecordDoubles * 8));
-#pragma unroll
-          for (int k = 0; k < 5; k++) cp_async16(dst + 16 * k, src + 16 * k);
-        }
-        cp_async_commit();
-        return true;
-      };
-      auto next_ring = [&](int from) -> int {  // first unfinished ring at or after `from` in the rotation (-1: none)
-#pragma unroll
-        for (int k = 0; k < kRingsPerConsumer; k++) {
-          const int r = (from + k) % kRingsPerConsumer;
-          if (!(finished & (1u << r))) return r;
-        }
-        return -1;
-      };
-
-      Bat cur{0u, 0u, 0, false, false}, nxt{0u, 0u, 0, false, false};
-      while (true) {
-        if (!cur.valid) {
-          const int r = next_ring(rot);
-          if (r < 0) break;
-          B2_T0(tw);
-          fetch(r, true, cur, buf);
-          B2_TACC(0, tw);
-          rot = (r + 1) % kRingsPerConsumer;
-#ifdef B2_V2_TIMING
-          tacc[4]++;
-#endif
-        }
-        // try to get the following batch on its way before computing this one
-        nxt.valid = false;
         {
-          const int r = next_ring(rot);
-          if (r >= 0 && fetch(r, false, nxt, buf ^ 1u)) rot = (r + 1) % kRingsPerConsumer;
+          B2_T0(tw);
+          Backoff bo(32u, 128u);
+          while (true) {
+            const uint32_t dn = ld_acquire(&sh.done[p]);
+            const uint32_t tl = ld_acquire(&sh.tail[p]);
+            const uint32_t avail = tl - hd;
+            if (avail >= kBatch) {
+              nb = kBatch;
+              break;
+            }
+            if (dn == run) {  // the probe warp finished this run: `tl` is final
+              nb = avail;
+              fin = true;
+              break;
+            }
+            bo.wait();
+          }
+          B2_TACC(0, tw);
         }
-        B2_T0(t_cp);
-        if (nxt.valid)
-          cp_async_wait<1>();
-        else
-          cp_async_wait<0>();
-        B2_TACC(1, t_cp);
         B2_T0(t_comp);
 #ifdef B2_V2_TIMING
         tacc[5]++;
 #endif
-        // ---- compute `cur` from shared memory only ----
-        {
-          const int p = cw + cur.r * kC;
-          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
-          const bool valid = static_cast<uint32_t>(lane) < cur.nb;
-          const uint32_t slot = (cur.hd + lane) & (kRing - 1);
-          const double2 q0 = rg[slot], q1 = rg[kRing + slot];
-          const uint32_t loc = valid ? static_cast<uint32_t>(static_cast<unsigned long long>(__double_as_longlong(q1.y))) : 0u;
+        const bool valid = static_cast<uint32_t>(lane) < nb;
+        if (valid) {  // uniform for full batches
+          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1) + ((hd + lane) & (kRing - 1));
+          const double2 q0 = rg[0], q1 = rg[kRing];
 #ifndef B2_V2_DEBUG_NO_ACCUM
-          if (valid) {  // uniform for full batches
-            const double2* rr = reinterpret_cast<const double2*>(recbuf + buf * kRecBufBytes + lane * (kRecordDoubles * 8));
-            TargetRec T;
-            T.r01 = rr[0];
-            T.r23 = rr[1];
-            T.r45 = rr[2];
-            T.r67 = rr[3];
-            T.r89 = rr[4];
-            const uint32_t cs = loc / kTile, li = loc % kTile;
-            const CT* cp = reinterpret_cast<const CT*>(cov_stages + cs * CS::kBytes) + li;
-            SourceCov A;
-            A.a00 = static_cast<double>(cp[0]);
-            A.a01 = static_cast<double>(cp[kTile]);
-            A.a02 = static_cast<double>(cp[2 * kTile]);
-            A.a11 = static_cast<double>(cp[3 * kTile]);
-            A.a12 = static_cast<double>(cp[4 * kTile]);
-            A.a22 = static_cast<double>(cp[5 * kTile]);
-            accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
-          }
+          TargetRec T;
+          T.r01 = rg[2 * kRing];
+          T.r23 = rg[3 * kRing];
+          T.r45 = rg[4 * kRing];
+          T.r67 = rg[5 * kRing];
+          T.r89 = rg[6 * kRing];
+          const double2 c0 = rg[7 * kRing], c1 = rg[8 * kRing], c2 = rg[9 * kRing];
+          auto cell = [](double v) -> double {  // an 8-byte cell holds a double, or a float in its low half
+            return sizeof(CT) == 8 ? v : static_cast<double>(__int_as_float(__double2loint(v)));
+          };
+          SourceCov A;
+          A.a00 = cell(c0.x);
+          A.a01 = cell(c0.y);
+          A.a02 = cell(c1.x);
+          A.a11 = cell(c1.y);
+          A.a12 = cell(c2.x);
+          A.a22 = cell(c2.y);
+          accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
 #else
-          if (valid) acc[28] += q0.x * 0.0 + 1.0 + static_cast<double>(loc) * 0.0;  // measurement aid: probe-side throughput only
+          acc[28] += q0.x * 0.0 + 1.0 + q1.x * 0.0;  // measurement aid: probe-side throughput only
 #endif
-          // operands read: hand the ring slots (and the covariance stages behind them) back to the probe warp
-          __syncwarp();
-          if (lane == 0) {
-            st_release(&sh.head[p], cur.hd + cur.nb);
-            if (cur.fin) st_release(&sh.ack[p], run);
-          }
         }
+        // operands read: hand the ring slots back to the probe warp
+        __syncwarp();
+        if (lane == 0) {
+          st_release(&sh.head[p], hd + nb);
+          if (fin) st_release(&sh.ack[p], run);
+        }
+#pragma unroll
+        for (int k = 0; k < kRingsPerConsumer; k++)
+          if (k == r) head[k] = hd + nb;
+        if (fin) finished |= 1u << r;
+        r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
         B2_TACC(2, t_comp);
-        cur = nxt;
-        buf ^= 1u;
       }
       B2_T0(t_fl);
       flush_factor<MODE>(sh, acc, ctid, partials, counters, out, pe, sig);

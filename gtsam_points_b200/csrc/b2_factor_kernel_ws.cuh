@@ -221,7 +221,7 @@ template <typename PT, typename CT, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
               const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-              const DoneSignal sig, const PoseArg /*pose: by-value poses are a feature of the v2 kernel*/) {
+              const DoneSignal sig, const PoseArg /*pose: by-value poses are a feature of the v2 kernel*/, const uint32_t* __restrict__ frozen_flags) {
   __shared__ Shared sh;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double2* const rings = reinterpret_cast<double2*>(dyn_smem);
@@ -256,6 +256,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const uint32_t f_tile_begin = dg->tile_begin;
       const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
       const uint32_t out_index = dg->out_index;
+      // correspondence-update tolerance (integrated_gicp_factor_impl.hpp:135-147): the host decided that this factor's pose moved
+      // less than its tolerances since the last association -> keep the stored correspondences, linearize them at the new pose
+      const bool frozen = MODE == MODE_ERROR || (frozen_flags != nullptr && __ldg(frozen_flags + out_index) != 0u);
       const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
       const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
       const double* __restrict__ records = dg->records;
@@ -293,7 +296,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         if (base >= n) return;
         const uint32_t first = base + (lane % kLinesPerPlane) * (128 / sizeof(PT));  // first element of this lane's line
         if (lane < 3 * kLinesPerPlane && first < n_pad) prefetch_l2(px + (lane / kLinesPerPlane) * n_pad + first);
-        if (MODE == MODE_ERROR && lane >= 24 && lane < 24 + kWarpPoints / 32 && base + (lane - 24) * 32 < n_pad) prefetch_l2(corr + base + (lane - 24) * 32);
+        if (frozen && lane >= 24 && lane < 24 + kWarpPoints / 32 && base + (lane - 24) * 32 < n_pad) prefetch_l2(corr + base + (lane - 24) * 32);
       };
       uint32_t pt_cur = phys_tile(tile), pt_ahead = pt_cur;
       for (uint32_t k = 0; k < kPrefetchAhead; k++) {
@@ -318,7 +321,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           c.y[k] = __ldg(px + n_pad + j);
           c.z[k] = __ldg(px + 2 * n_pad + j);
           c.cid[k] = -1;
-          if (MODE == MODE_ERROR) c.cid[k] = __ldg(corr + j);
+          if (frozen) c.cid[k] = __ldg(corr + j);
         }
         return c;
       };
@@ -344,9 +347,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 #pragma unroll
         for (int k = 0; k < kPPL; k++) {
           ok[k] = base + k * 32 < n;
-          id[k] = (MODE == MODE_ERROR && ok[k]) ? c.cid[k] : -1;
+          id[k] = (frozen && ok[k]) ? c.cid[k] : -1;
           rotate_point(R, static_cast<double>(c.x[k]), static_cast<double>(c.y[k]), static_cast<double>(c.z[k]), u[k][0], u[k][1], u[k][2]);
-          if (MODE == MODE_LINEARIZE && KIND == 0) {
+          if (MODE == MODE_LINEARIZE && KIND == 0 && !frozen) {
             cx[k] = voxel_coord1(__dadd_rn(u[k][0], t[0]), inv_leaf);
             cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
             cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
@@ -359,7 +362,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         uint32_t mask[kPPL], cnt = 0u;
 #pragma unroll
         for (int k = 0; k < kPPL; k++) {
-          if (MODE == MODE_LINEARIZE) {
+          if (MODE == MODE_LINEARIZE && !frozen) {
             if (KIND == 0) {
 #ifdef B2_WS_DEBUG_NO_PROBE
               id[k] = static_cast<int>(grp_idx[k] & 0xffffu);  // measurement aid: no table access, every point "hits" some record

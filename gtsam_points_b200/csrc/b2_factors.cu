@@ -54,6 +54,7 @@ struct DoneSignal {
   // n_peers == 0: unused.  `flag` doubles as this GPU's own flag array in that mode.
   int n_peers;
   int my_rank;
+  int wait_in_kernel;  // the signalling thread also waits until every rank's flag in THIS GPU's array shows seq: the launch completes = the exchange completed
   double* peer_out[kMaxPeers];          // same offset as `out` of the launch, in each peer's buffer (entry my_rank unused)
   unsigned int* peer_flag[kMaxPeers];   // each GPU's flag array [n_peers]
 };
@@ -90,6 +91,19 @@ __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
     __threadfence_system();
     if (sig.n_peers > 0) {
       for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
+      if (sig.wait_in_kernel) {
+        // fold the flag wait into this launch (no second kernel): every other CTA of this GPU is done or draining, so one
+        // spinning thread costs nothing; bounded (a rank may still be loading its modules at the first step: ~30 s)
+        const volatile unsigned int* mine = sig.peer_flag[sig.my_rank];
+        for (int r = 0; r < sig.n_peers; r++) {
+          unsigned polls = 0;
+          while (mine[r] != sig.seq) {
+            __nanosleep(64);
+            if (++polls > (1u << 28)) __trap();
+          }
+        }
+        __threadfence_system();
+      }
     } else {
       *sig.flag = sig.seq;
     }
@@ -104,7 +118,7 @@ struct FactorDesc {
   // VGICP target
   const VoxelBucket* buckets;
   uint32_t bucket_mask;
-  uint32_t pad0;
+  uint32_t num_records;  // voxels in the map (length of `records` for the voxel path)
   double inv_leaf;
   // GICP target
   const KdNodeGPU* nodes;
@@ -382,10 +396,10 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_V2_CONSUMERS 8
 #endif
 #ifndef B2_V2_REGS_PRODUCER
-#define B2_V2_REGS_PRODUCER 88
+#define B2_V2_REGS_PRODUCER 104
 #endif
 #ifndef B2_V2_REGS_CONSUMER
-#define B2_V2_REGS_CONSUMER 136
+#define B2_V2_REGS_CONSUMER 120
 #endif
 #ifndef B2_V2_RING
 #define B2_V2_RING 128
@@ -394,19 +408,19 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_V2_PPL 2
 #endif
 #ifndef B2_V2_XYZ_STAGES
-#define B2_V2_XYZ_STAGES 3
+#define B2_V2_XYZ_STAGES 4
 #endif
-#ifndef B2_V2_COV_STAGES
-#define B2_V2_COV_STAGES 4
+#ifndef B2_V2_PREFETCH_GROUPS
+#define B2_V2_PREFETCH_GROUPS 0  // phase A starts every point's bucket group towards L2 (only useful with B2_V2_PIPELINE_A)
 #endif
-#ifndef B2_V2_COV_RETAIN
-#define B2_V2_COV_RETAIN 2
+#ifndef B2_V2_PIPELINE_A
+#define B2_V2_PIPELINE_A 0  // probe warps compute tile j + 1's hashes while tile j's bucket groups are in flight (costs registers)
+#endif
+#ifndef B2_V2_WARM_L2
+#define B2_V2_WARM_L2 1  // idle warps of the producer warpgroup stream the bucket table into L2 at kernel start
 #endif
 #ifndef B2_V2_REGS_AUX
 #define B2_V2_REGS_AUX 24
-#endif
-#ifndef B2_V2_PREFETCH_RECORDS
-#define B2_V2_PREFETCH_RECORDS 1  // probe warps start the voxel record lines of every hit towards L2
 #endif
 #include "b2_factor_kernel_v2.cuh"
 #undef B2_V2_NAMESPACE
@@ -453,7 +467,7 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: factor / factor-set objects
 // ---------------------------------------------------------------------------------------------------------------
-using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal, PoseArg);
+using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal, PoseArg, const uint32_t*);
 
 template <int MODE, bool SINGLE>
 KernelFn pick_vgicp(int pb, int cb) {
@@ -531,6 +545,8 @@ struct b2_factor_set {
   double* d_poses_eval = nullptr;  // F x 16
   double* d_out = nullptr;         // F x 128
   double* d_err = nullptr;         // F
+  uint32_t* d_frozen = nullptr;    // F: per factor, 1 = keep the stored correspondences in this linearize (correspondence-update tolerance)
+  bool any_tolerance = false;      // some factor of the set has a tolerance: the flags are maintained
   uint64_t launches = 0;
 };
 
@@ -585,7 +601,76 @@ b2_status wait_done(b2_ctx* ctx, unsigned int seq) {
 }
 
 // h_pose != nullptr: the set holds ONE factor and its pose (16 doubles, host memory) travels by value with the launch
-b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{}, const double* h_pose = nullptr) {
+// Eigen::AngleAxisd(R).angle() the way Eigen computes it (through the quaternion: 2 atan2(|vec|, |w|)), for the tolerance test
+double rotation_angle_rm(const double* T) {
+  const double m00 = T[0], m11 = T[5], m22 = T[10];
+  double w, q[3];
+  const double tr = m00 + m11 + m22;
+  if (tr > 0.0) {
+    double t = std::sqrt(tr + 1.0);
+    w = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (T[9] - T[6]) * t, q[1] = (T[2] - T[8]) * t, q[2] = (T[4] - T[1]) * t;
+  } else {
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > T[i * 5]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(T[i * 5] - T[j * 5] - T[k * 5] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    w = (T[k * 4 + j] - T[j * 4 + k]) * t;
+    q[j] = (T[j * 4 + i] + T[i * 4 + j]) * t;
+    q[k] = (T[k * 4 + i] + T[i * 4 + k]) * t;
+  }
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  return n != 0.0 ? 2.0 * std::atan2(n, std::fabs(w)) : 0.0;
+}
+
+// integrated_gicp_factor_impl.hpp:135-147 for every factor of a host-pose linearize: decides which factors keep their
+// correspondences (pose within the tolerances of the last association point), remembers the new association points, and
+// uploads the flags (stream-ordered before the launch).  Returns the device flag array, or nullptr if no factor has a tolerance.
+b2_status prepare_frozen_flags(b2_factor_set* s, const double* deltas, const uint32_t** out_flags) {
+  *out_flags = nullptr;
+  if (!s->any_tolerance) {
+    for (size_t i = 0; i < s->factors.size(); i++) {
+      std::memcpy(s->factors[i]->last_corr_delta, deltas + i * 16, sizeof(double) * 16);
+      s->factors[i]->has_corr = true;
+    }
+    return B2_OK;
+  }
+  const size_t F = s->factors.size();
+  std::vector<uint32_t> flags(F, 0u);
+  for (size_t i = 0; i < F; i++) {
+    b2_factor* f = s->factors[i];
+    const double* d = deltas + i * 16;
+    bool do_update = true;
+    if (f->kind != B2_FACTOR_VGICP && f->has_corr && (f->corr_tol_trans > 0.0 || f->corr_tol_rot > 0.0)) {
+      // diff = delta^-1 * last_correspondence_point
+      double diff[16] = {0};
+      const double* L = f->last_corr_delta;
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) diff[r * 4 + c] = d[0 * 4 + r] * L[0 * 4 + c] + d[1 * 4 + r] * L[1 * 4 + c] + d[2 * 4 + r] * L[2 * 4 + c];
+        diff[r * 4 + 3] = d[0 * 4 + r] * (L[3] - d[3]) + d[1 * 4 + r] * (L[7] - d[7]) + d[2 * 4 + r] * (L[11] - d[11]);
+      }
+      const double diff_rot = rotation_angle_rm(diff);
+      const double diff_trans = std::sqrt(diff[3] * diff[3] + diff[7] * diff[7] + diff[11] * diff[11]);
+      if (diff_rot < f->corr_tol_rot && diff_trans < f->corr_tol_trans) do_update = false;
+    }
+    if (do_update) {
+      std::memcpy(f->last_corr_delta, d, sizeof(double) * 16);
+      f->has_corr = true;
+    } else {
+      flags[i] = 1u;
+    }
+  }
+  B2_CUDA(cudaMemcpyAsync(s->d_frozen, flags.data(), F * sizeof(uint32_t), cudaMemcpyHostToDevice, s->ctx->stream));  // pageable source: staged before return
+  *out_flags = s->d_frozen;
+  return B2_OK;
+}
+
+b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const double* d_eval, double* d_out, DoneSignal sig = DoneSignal{}, const double* h_pose = nullptr,
+                        const uint32_t* d_frozen = nullptr) {
   cudaStream_t st = s->ctx->stream;
   PoseArg pa{};
   const bool single = h_pose != nullptr && s->factors.size() == 1 && s->groups.size() == 1 && s->groups[0].fn_single[mode] != nullptr;
@@ -605,6 +690,7 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
           d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets / kGroup - 1);
           d.inv_leaf = f->voxelmap->inv_resolution;
           d.records = f->voxelmap->d_records;
+          d.num_records = static_cast<uint32_t>(f->voxelmap->num_voxels);
         }
         B2_CUDA(cudaMemcpyAsync(&g.d_descs[k], &d, sizeof(FactorDesc), cudaMemcpyHostToDevice, st));
         g.gen[k] = f->params_gen;
@@ -612,7 +698,7 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
       }
     }
     (single ? g.fn_single[mode] : g.fn[mode])<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem[mode], st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials,
-                                                                                                                  s->d_counters, d_out, sig, pa);
+                                                                                                                  s->d_counters, d_out, sig, pa, d_frozen);
     s->launches++;
   }
   B2_CUDA(cudaGetLastError());
@@ -725,6 +811,16 @@ b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist) {
   return B2_OK;
 }
 
+b2_status b2_factor_set_correspondence_update_tolerance(b2_factor* f, double angle, double trans) {
+  B2_REQUIRE(f != nullptr, "b2_factor_set_correspondence_update_tolerance: factor is NULL");
+  B2_REQUIRE(f->kind != B2_FACTOR_VGICP, "b2_factor_set_correspondence_update_tolerance: the VGICP factor has no correspondence-update tolerance (integrated_vgicp_factor.hpp)");
+  B2_REQUIRE(angle >= 0.0 && trans >= 0.0, "b2_factor_set_correspondence_update_tolerance: negative tolerance");
+  f->corr_tol_rot = angle;  // integrated_gicp_factor.hpp:106-109
+  f->corr_tol_trans = trans;
+  if (f->self_set) f->self_set->any_tolerance = true;
+  return B2_OK;
+}
+
 size_t b2_factor_num_points(const b2_factor* f) { return f ? f->source->n : 0; }
 
 b2_status b2_factor_correspondences(const b2_factor* f, int64_t* out) {
@@ -806,6 +902,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
         d.bucket_mask = static_cast<uint32_t>(f->voxelmap->num_buckets / kGroup - 1);  // group mask
         d.inv_leaf = f->voxelmap->inv_resolution;
         d.records = f->voxelmap->d_records;
+        d.num_records = static_cast<uint32_t>(f->voxelmap->num_voxels);
       } else {
         d.nodes = f->tree->d_nodes;
         d.leaf_pts = f->tree->d_leaf_points;
@@ -873,12 +970,14 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       (e = cudaMalloc(reinterpret_cast<void**>(&s->d_poses_lin), F * 16 * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&s->d_poses_eval), F * 16 * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&s->d_out), F * B2_LINEARIZED_DOUBLES * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_err), F * sizeof(double))) != cudaSuccess) {
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_err), F * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&s->d_frozen), F * sizeof(uint32_t))) != cudaSuccess) {
     return fail_cleanup(fail(B2_ERR_OUT_OF_MEMORY, "b2_factor_set_create: %s", cudaGetErrorString(e)));
   }
   if ((e = cudaMemsetAsync(s->d_counters, 0, F * sizeof(unsigned int), st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) {
     return fail_cleanup(fail(B2_ERR_CUDA, "b2_factor_set_create: %s", cudaGetErrorString(e)));
   }
+  for (size_t i = 0; i < F; i++) s->any_tolerance |= factors[i]->corr_tol_rot > 0.0 || factors[i]->corr_tol_trans > 0.0;
   b2_status ss = ctx->ensure_stage(F * (B2_LINEARIZED_DOUBLES + 32) * sizeof(double), 0);
   if (ss != B2_OK) return fail_cleanup(ss);
   *out = s;
@@ -899,6 +998,7 @@ b2_status b2_factor_set_destroy(b2_factor_set* s) {
   if (s->d_poses_eval) cudaFree(s->d_poses_eval);
   if (s->d_out) cudaFree(s->d_out);
   if (s->d_err) cudaFree(s->d_err);
+  if (s->d_frozen) cudaFree(s->d_frozen);
   delete s;
   return B2_OK;
 }
@@ -931,12 +1031,14 @@ b2_status b2_factor_set_issue_linearize(b2_factor_set* s, const double* deltas, 
   B2_CUDA(cudaSetDevice(s->ctx->device));
   const size_t F = s->factors.size();
   if (d_out == nullptr) d_out = s->d_out;
+  const uint32_t* d_frozen = nullptr;
+  B2_TRY(prepare_frozen_flags(s, deltas, &d_frozen));
   if (F == 1 && s->groups[0].fn_single[MODE_LINEARIZE] != nullptr) {
     B2_TRY(launch_groups(s, MODE_LINEARIZE, nullptr, nullptr, d_out, DoneSignal{}, deltas));  // pose by value: nothing but the launch
   } else {
     // pageable source: the runtime stages it before returning, so the caller's buffer is free immediately
     B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, deltas, F * 16 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
-    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out, DoneSignal{}, nullptr, d_frozen));
   }
   for (size_t i = 0; i < F; i++) {
     s->factors[i]->linearized = true;
@@ -1060,6 +1162,135 @@ b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers
   return B2_OK;
 }
 
+// ---- exchange objects: peer-mapped result blocks through CUDA IPC / peer access, no framework above the ABI ------------------
+}  // extern "C"
+
+struct b2_exchange {
+  b2_ctx* ctx = nullptr;
+  int n = 1, rank = 0;
+  size_t num_records = 0;
+  double* d_block = nullptr;          // [2][num_records][128] doubles, then 2 x 8 flag words (padded to 256 bytes)
+  double* peer_block[kMaxPeers] = {nullptr};
+  bool ipc_opened[kMaxPeers] = {false};
+  size_t rec_doubles() const { return num_records * B2_LINEARIZED_DOUBLES; }
+  size_t bytes() const { return 2 * rec_doubles() * sizeof(double) + 256; }
+};
+
+extern "C" {
+
+b2_status b2_exchange_create(b2_ctx* ctx, int n_ranks, int my_rank, size_t num_records, b2_exchange** out) {
+  B2_REQUIRE(out != nullptr, "b2_exchange_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_exchange_create: ctx is NULL");
+  B2_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeers && my_rank >= 0 && my_rank < n_ranks, "b2_exchange_create: bad rank %d of %d (at most %d GPUs of one node)", my_rank, n_ranks, kMaxPeers);
+  B2_REQUIRE(num_records > 0, "b2_exchange_create: num_records must be positive");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  b2_exchange* ex = new b2_exchange;
+  ex->ctx = ctx, ex->n = n_ranks, ex->rank = my_rank, ex->num_records = num_records;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->d_block), ex->bytes());
+  if (e == cudaSuccess) e = cudaMemset(ex->d_block, 0, ex->bytes());
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    if (ex->d_block) cudaFree(ex->d_block);
+    delete ex;
+    return fail(B2_ERR_OUT_OF_MEMORY, "b2_exchange_create: %s", cudaGetErrorString(e));
+  }
+  ex->peer_block[my_rank] = ex->d_block;
+  *out = ex;
+  return B2_OK;
+}
+
+b2_status b2_exchange_destroy(b2_exchange* ex) {
+  if (!ex) return B2_OK;
+  cudaSetDevice(ex->ctx->device);
+  cudaStreamSynchronize(ex->ctx->stream);
+  for (int p = 0; p < ex->n; p++)
+    if (ex->ipc_opened[p]) cudaIpcCloseMemHandle(ex->peer_block[p]);
+  if (ex->d_block) cudaFree(ex->d_block);
+  delete ex;
+  return B2_OK;
+}
+
+b2_status b2_exchange_export(const b2_exchange* ex, unsigned char handle[B2_IPC_HANDLE_BYTES]) {
+  B2_REQUIRE(ex && handle, "b2_exchange_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == B2_IPC_HANDLE_BYTES, "IPC handle size");
+  B2_CUDA(cudaSetDevice(ex->ctx->device));
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, ex->d_block));
+  std::memcpy(handle, &h, sizeof(h));
+  return B2_OK;
+}
+
+b2_status b2_exchange_import(b2_exchange* ex, int peer_rank, const unsigned char handle[B2_IPC_HANDLE_BYTES]) {
+  B2_REQUIRE(ex && handle, "b2_exchange_import: NULL argument");
+  B2_REQUIRE(peer_rank >= 0 && peer_rank < ex->n && peer_rank != ex->rank, "b2_exchange_import: bad peer rank %d", peer_rank);
+  B2_CUDA(cudaSetDevice(ex->ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  B2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ex->peer_block[peer_rank] = static_cast<double*>(p);
+  ex->ipc_opened[peer_rank] = true;
+  return B2_OK;
+}
+
+b2_status b2_exchange_enable_peer(b2_exchange* ex, int peer_rank, const b2_exchange* peer) {
+  B2_REQUIRE(ex && peer, "b2_exchange_enable_peer: NULL argument");
+  B2_REQUIRE(peer_rank >= 0 && peer_rank < ex->n && peer_rank != ex->rank && peer->rank == peer_rank && peer->num_records == ex->num_records, "b2_exchange_enable_peer: mismatched exchange objects");
+  B2_CUDA(cudaSetDevice(ex->ctx->device));
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(B2_ERR_CUDA, "b2_exchange_enable_peer: %s", cudaGetErrorString(e));
+  (void)cudaGetLastError();
+  ex->peer_block[peer_rank] = peer->d_block;
+  return B2_OK;
+}
+
+const double* b2_exchange_records(const b2_exchange* ex, unsigned int step) { return ex ? ex->d_block + (step & 1u) * ex->rec_doubles() : nullptr; }
+
+b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* s, const double* deltas, size_t first_slot, unsigned int step) {
+  B2_REQUIRE(ex != nullptr, "b2_exchange_linearize: exchange is NULL");
+  B2_REQUIRE(step != 0u, "b2_exchange_linearize: step starts at 1");
+  for (int p = 0; p < ex->n; p++) B2_REQUIRE(ex->peer_block[p] != nullptr, "b2_exchange_linearize: rank %d has not been imported", p);
+  const size_t F = s ? s->factors.size() : 0;
+  B2_REQUIRE(F == 0 || deltas != nullptr, "b2_exchange_linearize: deltas is NULL");
+  B2_REQUIRE(first_slot + F <= ex->num_records, "b2_exchange_linearize: slots [%zu, %zu) exceed the %zu records of the exchange", first_slot, first_slot + F, ex->num_records);
+  B2_CUDA(cudaSetDevice(ex->ctx->device));
+  const unsigned par = step & 1u;
+  DoneSignal sig{};
+  sig.n_peers = ex->n;
+  sig.my_rank = ex->rank;
+  sig.seq = step;
+  sig.wait_in_kernel = 1;
+  for (int p = 0; p < ex->n; p++) {
+    sig.peer_out[p] = ex->peer_block[p] + par * ex->rec_doubles() + first_slot * B2_LINEARIZED_DOUBLES;
+    sig.peer_flag[p] = reinterpret_cast<unsigned int*>(ex->peer_block[p] + 2 * ex->rec_doubles()) + par * 8;
+  }
+  if (F == 0) {  // nothing to linearize on this rank: still take part (raise, then wait)
+    raise_flags_kernel<<<1, 32, 0, ex->ctx->stream>>>(sig);
+    wait_flags_kernel<<<1, 32, 0, ex->ctx->stream>>>(sig.peer_flag[ex->rank], ex->n, step);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+  }
+  B2_REQUIRE(s->ctx == ex->ctx, "b2_exchange_linearize: set and exchange live on different contexts");
+  sig.counter = s->ctx->d_done_counter;
+  sig.flag = sig.peer_flag[ex->rank];
+  sig.total = static_cast<unsigned int>(F);
+  const uint32_t* d_frozen = nullptr;
+  B2_TRY(prepare_frozen_flags(s, deltas, &d_frozen));
+  double* d_out = sig.peer_out[ex->rank];
+  if (F == 1 && s->groups[0].fn_single[MODE_LINEARIZE] != nullptr) {
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, nullptr, nullptr, d_out, sig, deltas));
+  } else {
+    B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, deltas, F * 16 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, d_out, sig, nullptr, d_frozen));
+  }
+  for (size_t i = 0; i < F; i++) {
+    s->factors[i]->linearized = true;
+    std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
+  }
+  return B2_OK;
+}
+
 b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_linearized* out) {
   B2_REQUIRE(s && deltas && out, "b2_factor_set_linearize: NULL argument");
   static const bool trace = std::getenv("B2_TRACE") != nullptr;  // development aid: host-side time split of this call on stderr
@@ -1072,6 +1303,8 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
   char* h = static_cast<char*>(s->ctx->h_stage);
   std::memcpy(h, deltas, in_bytes);
   auto t1 = t0, t2 = t0;
+  const uint32_t* d_frozen = nullptr;
+  B2_TRY(prepare_frozen_flags(s, deltas, &d_frozen));
   if (F <= kZeroCopyMaxFactors) {
     // Small sets: ONE launch and one stream sync.  The staging buffer is pinned, mapped host memory: the kernel reads the
     // poses straight from it (128 B per factor over PCIe) and its per-factor epilogue writes the 1 KiB result record
@@ -1084,13 +1317,13 @@ b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_lin
     t1 = std::chrono::steady_clock::now();
     DoneSignal sig{};
     sig.counter = s->ctx->d_done_counter, sig.flag = s->ctx->d_done_flag, sig.total = static_cast<unsigned int>(F), sig.seq = ++s->ctx->done_seq;
-    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig, F == 1 ? deltas : nullptr));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, d_in, d_in, d_res, sig, F == 1 ? deltas : nullptr, d_frozen));
     t2 = std::chrono::steady_clock::now();
     B2_TRY(wait_done(s->ctx, sig.seq));
   } else {
     B2_CUDA(cudaMemcpyAsync(s->d_poses_lin, h, in_bytes, cudaMemcpyHostToDevice, st));
     t1 = std::chrono::steady_clock::now();
-    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out));
+    B2_TRY(launch_groups(s, MODE_LINEARIZE, s->d_poses_lin, s->d_poses_lin, s->d_out, DoneSignal{}, nullptr, d_frozen));
     B2_CUDA(cudaMemcpyAsync(h + in_bytes, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     t2 = std::chrono::steady_clock::now();
     B2_CUDA(cudaStreamSynchronize(st));

@@ -142,6 +142,10 @@ struct b2_factor {
   const b2_kdtree* tree = nullptr;
   const b2_cloud* source = nullptr;
   double max_corr_sq = 1.0;
+  // integrated_gicp_factor.hpp:103-109: skip re-association while the pose stays within these of the last association point
+  double corr_tol_rot = 0.0, corr_tol_trans = 0.0;
+  double last_corr_delta[16] = {0};
+  bool has_corr = false;  // correspondences have been established at last_corr_delta
   uint64_t params_gen = 0;  // bumped by every setter that changes a value factor sets have copied into their device descriptors
   int32_t* d_corr = nullptr;       // per stored source position: voxel id / target leaf position, -1 = none
   double* d_target_records = nullptr;  // GICP: target records in leaf order (Nt x 10), owned

@@ -115,65 +115,61 @@ class ShardedFactorSet:
 
     # -- multi-GPU exchange fused into the kernel's epilogue (peer stores over NVLink instead of an NCCL all-reduce) -----
     def _setup_peer_exchange(self):
-        """Symmetric (peer-mapped) result buffers: 2 x [num_global x 128] float64 (double-buffered by step parity) followed
-        by 2 x 8 uint32 flag words, identical layout on every rank.  torch's symmetric memory provides the allocation and
-        the exchange of peer pointers -- plumbing only; every byte is moved by this library's kernel.  Falls back to the
-        all-reduce path if symmetric memory is unavailable (B2_NO_PEER_EXCHANGE=1 forces that)."""
+        """b2_exchange: every rank owns a double-buffered [2 x num_global x 128] float64 block + flag words and maps every
+        peer's block through CUDA IPC (include/b2points.h).  torch.distributed only carries the 64-byte handles (one
+        all_gather_object at construction): every record byte is moved by this library's kernel, and the kernel itself waits
+        for the peers' flags.  Falls back to the all-reduce path if IPC is unavailable (B2_NO_PEER_EXCHANGE=1 forces that)."""
+        import ctypes as C
         import os
 
         if os.environ.get("B2_NO_PEER_EXCHANGE"):
             return
         torch, dist = self.torch, self.dist
         try:
-            import torch.distributed._symmetric_memory as symm_mem
-
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
             if world > 8:
                 return
-            rec_doubles = self.num_global * RECORD
-            flag_doubles = 32  # 256 bytes: 2 parities x 8 flag words (uint32), padded
-            buf = symm_mem.empty(2 * rec_doubles + flag_doubles, dtype=torch.float64, device=self.device)
-            buf.zero_()
-            group = self.group if self.group is not None else dist.group.WORLD
-            hdl = symm_mem.rendezvous(buf, group)
-            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            h = C.c_void_p()
+            capi.check(capi.lib().b2_exchange_create(self.ctx.h, world, rank, self.num_global, C.byref(h)))
+            handle = (C.c_ubyte * 64)()
+            capi.check(capi.lib().b2_exchange_export(h, handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=self.group)
+            for r, hb in enumerate(handles):
+                if r != rank:
+                    capi.check(capi.lib().b2_exchange_import(h, r, (C.c_ubyte * 64).from_buffer_copy(hb)))
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)  # every rank zeroed its flags before anybody raises one
-            self.exchange = dict(buf=buf, hdl=hdl, ptrs=ptrs, world=world, rank=rank, rec_doubles=rec_doubles)
+            self.exchange = dict(h=h, world=world, rank=rank)
         except Exception as e:  # pragma: no cover - depends on the driver / topology of the box
             import warnings
 
             warnings.warn(f"peer-memory exchange unavailable, using all-reduce: {e!r}")
             self.exchange = None
 
-    def _linearize_exchange(self):
-        import ctypes as C
-
+    def _linearize_exchange(self, h_deltas=None):
+        """One launch per step: linearize the local factors, store their records into every rank's block, raise the flags and
+        (inside the same kernel) wait for every rank's flag.  Poses are taken from the HOST (h_deltas, F_local x 16)."""
         ex = self.exchange
         self.step += 1
-        par = self.step & 1
-        world, rank, nrec = ex["world"], ex["rank"], ex["rec_doubles"]
-        out_off = (par * nrec + self.first * RECORD) * 8          # this rank's slots in the parity buffer (bytes)
-        flag_off = (2 * nrec) * 8 + par * 32                      # this parity's flag words (8 x uint32)
-        peer_out = (C.c_void_p * world)(*[p + out_off for p in ex["ptrs"]])
-        peer_flag = (C.c_void_p * world)(*[p + flag_off for p in ex["ptrs"]])
+        if h_deltas is None:
+            h_deltas = self.d_deltas.cpu().numpy()
+        h_deltas = np.ascontiguousarray(h_deltas, dtype=np.float64)
         self._enter_lib()
-        if self.local_factors:
-            capi.check(capi.lib().b2_factor_set_linearize_exchange(self.set.h, self.d_deltas.data_ptr(), ex["ptrs"][rank] + out_off, peer_out, peer_flag, world, rank, self.step))
-        else:  # nothing to linearize on this rank: still take part in the exchange
-            capi.check(capi.lib().b2_exchange_signal(self.ctx.h, peer_flag, world, rank, self.step))
-        capi.check(capi.lib().b2_exchange_wait(self.ctx.h, ex["ptrs"][rank] + flag_off, world, self.step))
+        capi.check(capi.lib().b2_exchange_linearize(ex["h"], self.set.h if self.local_factors else None, capi.dptr(h_deltas) if self.local_factors else None, self.first, self.step))
         self._leave_lib()
-        # NOTE: this view aliases the parity buffer of this step; it is overwritten two steps later (double-buffered by step parity)
-        self.d_all = ex["buf"][par * nrec : (par + 1) * nrec].view(self.num_global, RECORD)
+        ptr = capi.lib().b2_exchange_records(ex["h"], self.step)
+        # NOTE: this view aliases the parity block of this step; a peer overwrites it when it issues step + 2
+        self.d_all = _device_view(self.torch, ptr, (self.num_global, RECORD), self.device)
         return self.d_all
 
     # -- device-resident step: poses already in self.d_deltas -----------------------------------------------------
-    def linearize_device(self):
-        """Local kernel launch(es) + ONE all-reduce; leaves all records in self.d_all (device).  Asynchronous."""
+    def linearize_device(self, h_deltas=None):
+        """Local kernel launch(es) + the exchange; leaves all records in self.d_all (device).  Asynchronous.
+        h_deltas: the same poses as self.d_deltas on the HOST, if the caller has them (saves a read-back on the exchange path)."""
         torch, dist = self.torch, self.dist
         if self.exchange is not None:
-            return self._linearize_exchange()
+            return self._linearize_exchange(h_deltas)
         self.d_all.zero_()
         if self.local_factors:
             direct = self.compute is None and self.contiguous
@@ -193,11 +189,26 @@ class ShardedFactorSet:
     # -- end-to-end step: poses from the host, all records back on the host ---------------------------------------
     def linearize(self, deltas_local: np.ndarray) -> np.ndarray:
         torch = self.torch
+        hd = None
         if self.local_factors:
-            self.h_deltas[: len(self.local_factors)].copy_(torch.from_numpy(np.ascontiguousarray(deltas_local, dtype=np.float64).reshape(-1, 16)))
-            self.d_deltas.copy_(self.h_deltas, non_blocking=True)
-        self.linearize_device()
+            hd = np.ascontiguousarray(deltas_local, dtype=np.float64).reshape(-1, 16)
+            if self.exchange is None:
+                self.h_deltas[: len(self.local_factors)].copy_(torch.from_numpy(hd))
+                self.d_deltas.copy_(self.h_deltas, non_blocking=True)
+        self.linearize_device(hd)
         self.h_all.copy_(self.d_all, non_blocking=True)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         return self.h_all.numpy()
+
+
+def _device_view(torch, ptr: int, shape, device):
+    """A torch tensor over device memory this library owns (no copy, no ownership)."""
+
+    class _Ext:
+        pass
+
+    n = int(np.prod(shape))
+    holder = _Ext()
+    holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(holder, device=device).view(*shape)

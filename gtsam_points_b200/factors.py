@@ -192,10 +192,9 @@ class IntegratedGICPFactor(IntegratedMatchingCostFactor):
         capi.check(capi.lib().b2_factor_set_max_correspondence_distance(self.h, float(dist)))
 
     def set_correspondence_update_tolerance(self, angle: float, trans: float):
-        """integrated_gicp_factor.hpp:103-109: the reference may skip re-association when the pose moved less than these
-        tolerances (default 0 = always update).  The device path always re-associates -- the search is fused into the
-        linearization kernel -- i.e. it behaves like tolerance 0; the values are only stored."""
-        self.correspondence_update_tolerance = (float(angle), float(trans))
+        """integrated_gicp_factor.hpp:103-109, impl:135-147: while the pose stays within (angle, trans) of the pose of the
+        last correspondence update, linearize() keeps those correspondences and linearizes them at the new pose."""
+        capi.check(capi.lib().b2_factor_set_correspondence_update_tolerance(self.h, float(angle), float(trans)))
 
     def clone(self):
         a0 = self._keys[0] if self.is_binary else self.fixed_target_pose

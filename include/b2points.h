@@ -203,6 +203,12 @@ B2_API b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud
 B2_API b2_status b2_factor_destroy(b2_factor* f);
 /* IntegratedGICPFactor_::set_max_correspondence_distance (integrated_gicp_factor.hpp:98-101); default 1.0 */
 B2_API b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist);
+/* IntegratedGICPFactor_::set_correspondence_update_tolerance (integrated_gicp_factor.hpp:103-109, impl:135-147): a linearize()
+ * whose pose lies within (angle [rad], trans [m]) of the pose of the last correspondence update KEEPS those correspondences and
+ * linearizes them at the new pose; otherwise it re-associates.  Default 0 / 0 = always re-associate.  Honoured by the entry
+ * points that receive HOST poses (b2_factor_linearize, b2_factor_set_linearize, *_issue_linearize); the device-pose variants
+ * cannot see the pose and always re-associate.  Set it before the factor joins a user-built set.  kd-tree factors only. */
+B2_API b2_status b2_factor_set_correspondence_update_tolerance(b2_factor* f, double angle, double trans);
 B2_API size_t b2_factor_num_points(const b2_factor* f);
 /* Correspondences frozen at the last linearize, in the caller's point order: VGICP voxel id / GICP target index, -1 = none
  * (IntegratedVGICPFactor_::correspondences, integrated_vgicp_factor.hpp:107; IntegratedGICPFactor_::correspondences :147). */
@@ -267,6 +273,26 @@ B2_API b2_status b2_factor_set_linearize_exchange(b2_factor_set* set, const doub
 B2_API b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers, unsigned int seq);
 /* For a rank that owns no factor in this step: only raises peer_flags[p][my_rank] = seq on every GPU (stream-ordered). */
 B2_API b2_status b2_exchange_signal(b2_ctx* ctx, unsigned int* const* peer_flags, int n_peers, int my_rank, unsigned int seq);
+/* Peer-buffer setup for that exchange WITHOUT any framework above the ABI (what a C++ host such as ISAM2Ext needs,
+ * src/gtsam_points/optimizers/isam2_ext.cpp:110-129): every rank (one process per GPU) creates an exchange object holding its
+ * own double-buffered result block [2 x num_records x 128 doubles] + flag words, exports a 64-byte CUDA IPC handle, hands it to
+ * its peers over whatever channel it has (MPI, a pipe, shared memory ...), and imports theirs; b2_exchange_enable_peer maps a
+ * peer that lives in the SAME process (one thread per GPU) through cudaDeviceEnablePeerAccess instead.  b2_exchange_linearize is
+ * then one call per step: the factors of `set` are linearized, their records stored at slots first_slot.. of EVERY rank's
+ * block, flags raised, and the kernel itself waits for all ranks' flags before it completes -- when the stream reaches the
+ * end of this launch, b2_exchange_records(ex) holds all num_records records of the step.  step must increase by 1 per call,
+ * starting at 1, identically on every rank. */
+typedef struct b2_exchange b2_exchange;
+#define B2_IPC_HANDLE_BYTES 64
+B2_API b2_status b2_exchange_create(b2_ctx* ctx, int n_ranks, int my_rank, size_t num_records, b2_exchange** out);
+B2_API b2_status b2_exchange_destroy(b2_exchange* ex);
+B2_API b2_status b2_exchange_export(const b2_exchange* ex, unsigned char handle[B2_IPC_HANDLE_BYTES]);
+B2_API b2_status b2_exchange_import(b2_exchange* ex, int peer_rank, const unsigned char handle[B2_IPC_HANDLE_BYTES]);
+B2_API b2_status b2_exchange_enable_peer(b2_exchange* ex, int peer_rank, const b2_exchange* peer_in_this_process);
+/* deltas: HOST poses of the set's factors (F x 16), or NULL for a rank that owns no factor in this step (set may then be NULL) */
+B2_API b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* set, const double* deltas, size_t first_slot, unsigned int step);
+/* device pointer to the [num_records x 128] block of `step` (valid until step + 2 is issued) */
+B2_API const double* b2_exchange_records(const b2_exchange* ex, unsigned int step);
 /* Number of kernel launches issued by this set since creation (for bench.py's gpu_launches). */
 B2_API uint64_t b2_factor_set_launch_count(const b2_factor_set* set);
 

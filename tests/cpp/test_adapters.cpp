@@ -1,6 +1,11 @@
 // test_adapters.cpp -- exercises the C++ adapter classes (gtsam_points_b200.hpp) exactly in the call order the reference's
-// optimizers use (LinearizationHook: set.add(f) -> set.linearize(values) -> f->linearize(values) -> set.error(values) -> f->error(values)).
-// Inputs and expected values come from a binary file written by tests/test_cpp_adapters.py (oracle results).
+// optimizers use (LinearizationHook: set.add(f) -> set.linearize(values) -> f->linearize(values) -> set.error(values) -> f->error(values)),
+// plus the NonlinearFactorGPU issue / sync / store protocol, clone(), the frame-shaped constructors, k-NN and the map utilities.
+// Built twice by tests/test_cpp_adapters.py:
+//   * standalone (no GTSAM in the image): Pose / Values / HessianFactor stand-ins of the header;
+//   * with -I tests/cpp/mock_gtsam: the GTSAM-typed branch (gtsam::NonlinearFactor base, gtsam::Values / Pose3 / HessianFactor,
+//     gtsam_points::NonlinearFactorSet + LinearizationHook::register_hook) compiled and RUN against header mocks.
+// Inputs and expected values come from a binary file written by the python test (oracle results).
 //   usage: test_adapters <case.bin>
 #include <cmath>
 #include <cstdio>
@@ -28,6 +33,97 @@ static double relerr(const double* a, const double* b, int n) {
   return num / std::fmax(den, 1e-300);
 }
 
+// the reference's frame shape (types/point_cloud.hpp:103-118): raw pointers to Vector4d / Matrix4d arrays + size()
+struct Vec4d {
+  double v[4];
+};
+struct Mat4d {
+  double m[16];
+};
+struct FrameLike {
+  std::size_t num_points = 0;
+  Vec4d* points = nullptr;
+  Mat4d* covs = nullptr;
+  std::size_t size() const { return num_points; }
+};
+
+// ---- differences between the two builds, in one place ----
+#ifdef B2_HAVE_GTSAM
+static void insert_pose(Values& values, Key k, const std::vector<double>& T) {
+  gtsam::Matrix4 m;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) m(i, j) = T[i * 4 + j];
+  values.insert(k, gtsam::Pose3(m));
+}
+static FixedPose fixed_pose(const std::vector<double>& T) {
+  gtsam::Matrix4 m;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) m(i, j) = T[i * 4 + j];
+  return gtsam::Pose3(m);
+}
+struct Hess {  // row-major copies of the blocks of a gtsam::HessianFactor
+  double G11[36], G12[36], G22[36], g1[6], g2[6], f;
+  bool binary;
+};
+static Hess unpack(const LinearFactorPtr& lf) {
+  auto h = factor_pointer_cast<gtsam::HessianFactor>(lf);
+  Hess o{};
+  o.binary = h->keys().size() == 2;
+  for (int i = 0; i < 6; i++) {
+    for (int j = 0; j < 6; j++) {
+      o.G22[i * 6 + j] = h->G22(i, j);
+      if (o.binary) o.G11[i * 6 + j] = h->G11(i, j), o.G12[i * 6 + j] = h->G12(i, j);
+    }
+    o.g2[i] = h->g2(i);
+    if (o.binary) o.g1[i] = h->g1(i);
+  }
+  o.f = h->f;
+  return o;
+}
+#else
+static void insert_pose(Values& values, Key k, const std::vector<double>& T) {
+  Mat4 a;
+  std::copy(T.begin(), T.end(), a.begin());
+  values.insert(k, a);
+}
+static FixedPose fixed_pose(const std::vector<double>& T) {
+  Mat4 a;
+  std::copy(T.begin(), T.end(), a.begin());
+  return a;
+}
+struct Hess {
+  double G11[36], G12[36], G22[36], g1[6], g2[6], f;
+  bool binary;
+};
+static Hess unpack(const LinearFactorPtr& h) {
+  Hess o{};
+  o.binary = h->keys.size() == 2;
+  std::memcpy(o.G11, h->G11, sizeof(o.G11));
+  std::memcpy(o.G12, h->G12, sizeof(o.G12));
+  std::memcpy(o.G22, h->G22, sizeof(o.G22));
+  std::memcpy(o.g1, h->g1, sizeof(o.g1));
+  std::memcpy(o.g2, h->g2, sizeof(o.g2));
+  o.f = h->f;
+  return o;
+}
+#endif
+
+static int check_against(const Hess& h, const std::vector<double>& e, double tol) {
+  int fails = 0;
+  fails += relerr(h.G11, e.data(), 36) > tol;
+  fails += relerr(h.G22, e.data() + 36, 36) > tol;
+  fails += relerr(h.G12, e.data() + 72, 36) > tol;
+  double g1[6], g2[6];
+  for (int i = 0; i < 6; i++) {
+    g1[i] = -e[108 + i];
+    g2[i] = -e[114 + i];
+  }
+  fails += relerr(h.g1, g1, 6) > tol;
+  fails += relerr(h.g2, g2, 6) > tol;
+  fails += std::fabs(h.f - e[120]) > tol * e[120];
+  return fails;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   FILE* f = fopen(argv[1], "rb");
@@ -36,68 +132,152 @@ int main(int argc, char** argv) {
   const auto Tt = read_vec(f), Ts = read_vec(f), Ts2 = read_vec(f);
   const auto exp_vgicp = read_vec(f), exp_gicp = read_vec(f), exp_err = read_vec(f);
   const auto res = read_vec(f);
+  const auto exp_unary = read_vec(f), exp_overlap = read_vec(f);
   fclose(f);
   const std::size_t nt = tp.size() / 4, ns = sp.size() / 4;
-
-  auto target = std::make_shared<PointCloudGPU>(tp.data(), tc.data(), nt);
-  auto source = std::make_shared<PointCloudGPU>(sp.data(), sc.data(), ns);
-  auto voxels = std::make_shared<GaussianVoxelMapGPU>(res[0]);
-  voxels->insert(tp.data(), 4, tc.data(), 16, nt);
-  auto tree = std::make_shared<KdTreeGPU>(tp.data(), 4, nt);
-
-  auto vgicp = std::make_shared<IntegratedVGICPFactor>(0, 1, voxels, source);
-  auto gicp = std::make_shared<IntegratedGICPFactor>(0, 1, target, source, tree);
-  // the reference's tuning setters are accepted (source compatibility) and do not change results
-  vgicp->set_num_threads(4);
-  vgicp->set_fused_cov_cache_mode(FusedCovCacheMode::COMPACT);
-  gicp->set_num_threads(4);
-  gicp->set_fused_cov_cache_mode(FusedCovCacheMode::FULL);
-  gicp->set_correspondence_update_tolerance(0.0, 0.0);
-  if (vgicp->memory_usage() == 0 || gicp->memory_usage() == 0 || vgicp->get_target() != voxels) return 3;
-
-  Values values, values2;
-  Mat4 a, b, c;
-  std::copy(Tt.begin(), Tt.end(), a.begin());
-  std::copy(Ts.begin(), Ts.end(), b.begin());
-  std::copy(Ts2.begin(), Ts2.end(), c.begin());
-  values.insert(0, a);
-  values.insert(1, b);
-  values2.insert(0, a);
-  values2.insert(1, c);
-
-  NonlinearFactorSetGPU set;
-  if (!set.add(vgicp) || !set.add(gicp)) return 3;
-  auto lin = set.calc_linear_factors(values);
-  if (set.linearization_count() != 2) return 4;
   const double tol = 1e-9;
   int fails = 0;
-  const std::vector<double>* expd[2] = {&exp_vgicp, &exp_gicp};
-  for (int k = 0; k < 2; k++) {
-    const auto& e = *expd[k];
-    fails += relerr(lin[k]->G11, e.data(), 36) > tol;
-    fails += relerr(lin[k]->G22, e.data() + 36, 36) > tol;
-    fails += relerr(lin[k]->G12, e.data() + 72, 36) > tol;
-    double g1[6], g2[6];
-    for (int i = 0; i < 6; i++) {
-      g1[i] = -e[108 + i];
-      g2[i] = -e[114 + i];
-    }
-    fails += relerr(lin[k]->g1, g1, 6) > tol;
-    fails += relerr(lin[k]->g2, g2, 6) > tol;
-    fails += std::fabs(lin[k]->f - e[120]) > tol * e[120];
-  }
+
+  // frames in the reference's shape; the factors upload them once (PointCloudGPU::from_frame)
+  auto target_frame = std::make_shared<FrameLike>();
+  target_frame->num_points = nt;
+  target_frame->points = reinterpret_cast<Vec4d*>(const_cast<double*>(tp.data()));
+  target_frame->covs = reinterpret_cast<Mat4d*>(const_cast<double*>(tc.data()));
+  auto source_frame = std::make_shared<FrameLike>();
+  source_frame->num_points = ns;
+  source_frame->points = reinterpret_cast<Vec4d*>(const_cast<double*>(sp.data()));
+  source_frame->covs = reinterpret_cast<Mat4d*>(const_cast<double*>(sc.data()));
+  std::shared_ptr<const FrameLike> target_c = target_frame, source_c = source_frame;
+
+  auto voxels = std::make_shared<GaussianVoxelMapGPU>(res[0]);
+  voxels->insert(*target_frame);
+  GaussianVoxelMap::ConstPtr voxels_base = voxels;  // factors take the abstract map, like the reference
+
+  auto vgicp = std::make_shared<IntegratedVGICPFactor>(Key(0), Key(1), voxels_base, source_c);
+  auto gicp = std::make_shared<IntegratedGICPFactor>(Key(0), Key(1), target_c, source_c);
+  if (PointCloudGPU::from_frame(source_c) != PointCloudGPU::from_frame(source_c)) fails++;  // one device copy per frame
+  // the reference's tuning setters
+  vgicp->set_num_threads(4);
+  vgicp->set_fused_cov_cache_mode(FusedCovCacheMode::COMPACT);
+  vgicp->set_inlier_update_thresh(1e-3, 1e-3);
+  gicp->set_num_threads(4);
+  gicp->set_fused_cov_cache_mode(FusedCovCacheMode::FULL);
+  gicp->set_max_correspondence_distance(1.0);
+  if (vgicp->memory_usage() == 0 || gicp->memory_usage() == 0 || vgicp->get_target() != voxels || vgicp->dim() != 6) return 3;
+  vgicp->print("", &default_key_format);
+
+  Values values, values2;
+  insert_pose(values, 0, Tt);
+  insert_pose(values, 1, Ts);
+  insert_pose(values2, 0, Tt);
+  insert_pose(values2, 1, Ts2);
+
+  // ---- the batched set, through the interface the optimizers hold (NonlinearFactorSet) ----
+  std::shared_ptr<FactorSetBase> set = create_nonlinear_factor_set_gpu();
+#ifdef B2_HAVE_LINEARIZATION_HOOK
+  gtsam_points::LinearizationHook::register_hook([] { return create_nonlinear_factor_set_gpu(); });  // src/demo/demo_matching_cost_factors.cpp:52
+  if (gtsam_points::LinearizationHook::hook_constructors().size() != 1) fails++;
+  gtsam::NonlinearFactorGraph graph;
+  graph.add(vgicp);
+  graph.add(gicp);
+  set->add(graph);
+  if (set->size() != 2) return 3;
+#else
+  if (!set->add(vgicp) || !set->add(gicp)) return 3;
+#endif
+  auto lin = set->calc_linear_factors(values);
+  if (set->linearization_count() != 2) return 4;
+  fails += check_against(unpack(lin[0]), exp_vgicp, tol);
+  fails += check_against(unpack(lin[1]), exp_gicp, tol);
   if (vgicp->num_inliers() != static_cast<int>(exp_vgicp[121])) fails++;
   // error() after a batched evaluation returns the stored result (IntegratedVGICPFactorGPU::error semantics)
-  set.error(values2);
+  set->error(values2);
   fails += std::fabs(vgicp->error(values2) - exp_err[0]) > tol * exp_err[0];
   fails += std::fabs(gicp->error(values2) - exp_err[1]) > tol * exp_err[1];
   // ... and without a set the factor evaluates on its own (sync path)
   fails += std::fabs(vgicp->error(values2) - exp_err[0]) > tol * exp_err[0];
-  // single-query NearestNeighborSearch signature
-  std::size_t idx;
-  double sq;
-  const double q[3] = {tp[0] + 0.01, tp[1], tp[2]};
-  if (tree->knn_search(q, 1, &idx, &sq) != 1 || sq > 1e-3) fails++;
+
+  // ---- NonlinearFactorGPU protocol, driven the way nonlinear_factor_set_gpu.cpp:91-133 drives it ----
+  {
+    NonlinearFactorGPU& gf = *vgicp;
+    std::vector<unsigned char> lin_in(gf.linearization_input_size()), lin_out(gf.linearization_output_size()), ev_in(gf.evaluation_input_size()), ev_out(gf.evaluation_output_size());
+    void *d_lin_out = nullptr, *d_ev_out = nullptr;
+    b2_ctx* ctx = Context::default_context()->get();
+    check(b2_device_malloc(ctx, lin_out.size(), &d_lin_out), "malloc");
+    check(b2_device_malloc(ctx, ev_out.size(), &d_ev_out), "malloc");
+    gf.set_linearization_point(values, lin_in.data());
+    gf.issue_linearize(lin_in.data(), nullptr, d_lin_out);
+    gf.sync();
+    check(b2_memcpy_d2h(ctx, lin_out.data(), d_lin_out, lin_out.size()), "d2h");
+    gf.store_linearized(lin_out.data());
+    fails += check_against(unpack(vgicp->linearize(values)), exp_vgicp, tol);  // returns the stored linearization
+    gf.set_evaluation_point(values2, ev_in.data());
+    gf.issue_compute_error(lin_in.data(), ev_in.data(), nullptr, nullptr, d_ev_out);
+    gf.sync();
+    check(b2_memcpy_d2h(ctx, ev_out.data(), d_ev_out, ev_out.size()), "d2h");
+    gf.store_computed_error(ev_out.data());
+    fails += std::fabs(vgicp->error(values2) - exp_err[0]) > tol * exp_err[0];
+    b2_device_free(ctx, d_lin_out);
+    b2_device_free(ctx, d_ev_out);
+  }
+
+  // ---- clone() returns the base-class pointer and an independent, equivalent factor; unary form ----
+  {
+    FactorBasePtr c = vgicp->clone();
+    auto cv = factor_pointer_cast<IntegratedVGICPFactor>(c);
+    if (!cv || cv.get() == vgicp.get() || c->keys().size() != 2) fails++;
+    fails += check_against(unpack(c->linearize(values)), exp_vgicp, tol);
+    auto unary = std::make_shared<IntegratedVGICPFactor>(fixed_pose(Tt), Key(1), voxels_base, source_c);
+    const Hess hu = unpack(unary->linearize(values));
+    if (hu.binary) fails++;
+    fails += relerr(hu.G22, exp_unary.data() + 36, 36) > tol;
+    FactorBasePtr cu = unary->clone();
+    if (cu->keys().size() != 1 || cu->keys()[0] != Key(1)) fails++;
+    fails += relerr(unpack(cu->linearize(values)).G22, exp_unary.data() + 36, 36) > tol;
+  }
+
+  // ---- correspondence-update tolerance (integrated_gicp_factor.hpp:103-109): correspondences frozen inside the tolerance ----
+  {
+    auto g2 = std::make_shared<IntegratedGICPFactor>(Key(0), Key(1), target_c, source_c);
+    g2->set_correspondence_update_tolerance(0.5, 5.0);
+    g2->linearize(values);
+    const auto c0 = g2->correspondences();
+    g2->linearize(values2);
+    if (g2->correspondences() != c0) fails++;
+    g2->set_correspondence_update_tolerance(0.0, 0.0);
+    g2->linearize(values2);
+    auto g3 = std::make_shared<IntegratedGICPFactor>(Key(0), Key(1), target_c, source_c);
+    g3->linearize(values2);
+    if (g2->correspondences() != g3->correspondences()) fails++;
+  }
+
+  // ---- NearestNeighborSearch surface: k = 1 and k = 5, radius search ----
+  {
+    KdTreeGPU tree(tp.data(), 4, nt);
+    const NearestNeighborSearch& nn = tree;
+    std::size_t idx[5];
+    double sq[5];
+    const double q[3] = {tp[0] + 0.01, tp[1], tp[2]};
+    if (nn.knn_search(q, 1, idx, sq) != 1 || sq[0] > 1e-3) fails++;
+    if (nn.knn_search(q, 5, idx, sq) != 5 || !(sq[0] <= sq[1] && sq[1] <= sq[2] && sq[3] <= sq[4])) fails++;
+    std::vector<std::size_t> ri;
+    std::vector<double> rs;
+    const std::size_t found = nn.radius_search(q, 0.5, ri, rs);
+    if (found == 0 || found != ri.size() || rs.back() >= 0.25) fails++;
+  }
+
+  // ---- map utilities: overlap, save_compact / load ----
+  {
+    Mat4 I{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const double ov = overlap_gpu(voxels_base, PointCloudGPU::from_frame(source_c), calc_delta(pose_matrix(values, 0), pose_matrix(values, 1)));
+    fails += std::fabs(ov - exp_overlap[0]) > 1e-15;
+    if (overlap_gpu(voxels_base, PointCloudGPU::from_frame(target_c), I) < 0.99) fails++;
+    const std::string path = std::string(argv[1]) + ".voxels";
+    voxels_base->save_compact(path);
+    auto loaded = GaussianVoxelMapGPU::load(path);
+    if (!loaded || loaded->num_voxels() != voxels->num_voxels() || loaded->voxel_resolution() != voxels->voxel_resolution()) fails++;
+  }
+
   printf("%s (%d failed checks, vgicp inliers %d)\n", fails ? "FAIL" : "OK", fails, vgicp->num_inliers());
   return fails ? 1 : 0;
 }
