@@ -287,6 +287,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -311,10 +313,55 @@ def run_gpu(args):
 
     stream = torch.cuda.Stream(device=dev)
     K, W = args.steps, args.warmup
+    dp = C.POINTER(C.c_double)
+    L = capi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     with torch.cuda.stream(stream):
         ctx = g.Context(local_rank, stream=stream.cuda_stream)
+        # L2 flush between timed steps: write 256 MiB (> 126 MB of L2), then stream 256 MiB of other memory through it with
+        # reads so that the cache is left full of CLEAN foreign lines -- none of the workload's data is resident, and the timed
+        # kernel does not also pay for writing the flush buffer's dirty lines back to DRAM.
+        flush_w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush_r = torch.zeros(32 << 20, dtype=torch.int64, device=dev)
+
+        def flush_l2(i):
+            if not args.no_flush:
+                flush_w.fill_(i & 0xFF)
+                flush_r.sum()
+
+        def time_steps(step_fn, poses_c, warmup, steps):
+            """max-over-ranks device time of `steps` calls of step_fn(pose), L2 flushed before each, own CUDA events per step."""
+            for i in range(warmup):
+                step_fn(poses_c[i])
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i in range(steps):
+                flush_l2(i)
+                if world > 1:
+                    barrier()  # ranks enter the timed step together: the exchange must not absorb another rank's L2 flush
+                ev[i][0].record(stream)
+                step_fn(poses_c[warmup + i])
+                ev[i][1].record(stream)
+            barrier()
+            ms = np.array([a.elapsed_time(b) for a, b in ev])
+            return max_over_ranks(float(ms.sum())), ms
+
+        # ================= headline: one 1M-point factor per rank (weak scaling) =================
         tp, tc, sp, sc = make_inputs(rank)
         poses = make_poses(rank, K + W)
+        poses_c = [np.ascontiguousarray(p.reshape(1, 16)) for p in poses]
+        poses_p = [p.ctypes.data_as(dp) for p in poses_c]  # argument marshalling is not part of any measured call
         t0 = time.perf_counter()
         vm = g.GaussianVoxelMapGPU(RESOLUTION, ctx)
         vm.insert(g.PointCloud(tp, tc, ctx=ctx, flags=capi.B2_CLOUD_NO_REORDER))
@@ -323,92 +370,66 @@ def run_gpu(args):
         setup_s = time.perf_counter() - t0
         sset = ShardedFactorSet([factor], [rank], world, ctx=ctx)
         vinfo, cinfo = vm.info(), src.info()
-
-        # L2 flush between timed steps: write 256 MiB (> 126 MB of L2), then stream 256 MiB of other memory through it with
-        # reads so that the cache is left full of CLEAN foreign lines -- none of the workload's data is resident, and the timed
-        # kernel does not also pay for writing the flush buffer's dirty lines back to DRAM.
-        flush_w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        flush_r = torch.zeros(32 << 20, dtype=torch.int64, device=dev)
-
-        def flush_l2(i):
-            flush_w.fill_(i & 0xFF)
-            flush_r.sum()
-        d_poses = torch.as_tensor(poses.reshape(K + W, 16), device=dev)
         launches0 = sset.set.launch_count()
-        import ctypes as C
+        issue_linearize = L.b2_factor_set_issue_linearize
 
-        dp = C.POINTER(C.c_double)
-        poses_c = [np.ascontiguousarray(p.reshape(1, 16)) for p in poses]
-        poses_p = [p.ctypes.data_as(dp) for p in poses_c]  # argument marshalling is not part of any measured call
-        issue_linearize = capi.lib().b2_factor_set_issue_linearize
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize(dev)
-
-        # ---- device-resident arm: value ----
-        for i in range(W):
-            sset.d_deltas.copy_(d_poses[i : i + 1])
-            sset.linearize_device()
-            if world == 1:
-                capi.check(issue_linearize(sset.set.h, poses_p[i], sset.d_all.data_ptr()))
-        barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for i in range(K):
-            if not args.no_flush:
-                flush_l2(i)
-            sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
-            if world > 1:
-                barrier()  # ranks enter the timed step together: the collective must not absorb another rank's L2 flush
-            ev[i][0].record(stream)
-            if world == 1:
-                # single GPU: the step IS the kernel launch (no collective); the same events serve the roofline.  The asynchronous
-                # entry point (NonlinearFactorGPU's issue_linearize): host pose in (by value with the launch), record left on the device
-                capi.check(issue_linearize(sset.set.h, poses_p[W + i], sset.d_all.data_ptr()))
-            else:
-                sset.linearize_device()  # zero, kernel (records written in place), ONE all-reduce
-            ev[i][1].record(stream)
-        barrier()
-        step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-        dev_total_ms = float(step_ms.sum())
-        rec = sset.d_all.cpu().numpy()
-        exchange_path = "peer stores in the kernel epilogue (NVLink) + flag wait" if sset.exchange is not None else "ONE all-reduce of [N x 128] f64 (NCCL)"
+        if world == 1:
+            # single GPU: the step IS the kernel launch (no exchange).  The asynchronous entry point (NonlinearFactorGPU's
+            # issue_linearize): host pose in (by value with the launch), record left on the device
+            def dev_step(pose):
+                capi.check(issue_linearize(sset.set.h, pose.ctypes.data_as(dp), sset.d_all.data_ptr()))
+        else:
+            def dev_step(pose):
+                sset.linearize_device(pose)  # one launch: linearize + peer stores of the records + in-kernel flag wait
+        dev_total_ms, step_ms = time_steps(dev_step, poses_c, W, K)
+        rec = sset.d_all.cpu().numpy().copy()
+        exchange_path = "peer stores in the kernel epilogue (NVLink) + in-kernel flag wait (b2_exchange, CUDA IPC)" if sset.exchange is not None else "ONE all-reduce of [N x 128] f64 (NCCL)"
         if world > 1 and sset.exchange is not None:
             # untimed cross-check: the fused peer-memory exchange must deliver exactly what the all-reduce path delivers
             saved, sset.exchange = sset.exchange, None
             sset.d_all = torch.zeros((sset.num_global, capi.B2_LINEARIZED_DOUBLES), dtype=torch.float64, device=dev)
+            sset.d_deltas.copy_(torch.as_tensor(poses_c[-1], device=dev))
             ref_all = sset.linearize_device().clone()
             barrier()
             sset.exchange = saved
-            got_all = sset.linearize_device().clone()
+            got_all = sset.linearize_device(poses_c[-1]).clone()
             barrier()
             assert torch.equal(ref_all, got_all), "peer-memory exchange and all-reduce disagree"
         n_inliers = int(rec[rank, 121])
         launches_dev = sset.set.launch_count() - launches0
         if world == 1:
             kern_ms = step_ms
-        else:  # kernel-only timing for the roofline (same launches, no collective)
-            for i in range(K):
-                if not args.no_flush:
-                    flush_l2(i)
-                sset.d_deltas.copy_(d_poses[W + i : W + i + 1])
-                kev[i][0].record(stream)
-                capi.check(capi.lib().b2_factor_set_linearize_device(sset.set.h, sset.d_deltas.data_ptr(), sset.d_local.data_ptr()))
-                kev[i][1].record(stream)
-            barrier()
-            kern_ms = np.array([a.elapsed_time(b) for a, b in kev])
+        else:  # kernel-only timing for the roofline (same launch, no exchange)
+            def kern_step(pose):
+                capi.check(issue_linearize(sset.set.h, pose.ctypes.data_as(dp), sset.d_local.data_ptr()))
+            _, kern_ms = time_steps(kern_step, poses_c, 1, K)
+        kern_ms_mean = max_over_ranks(float(kern_ms.mean()))
+
+        # ---- untimed parity check of the headline workload against the CPU oracle (rank 0; indices bit-exact, H / b 1e-9) ----
+        parity = None
+        if rank == 0 and not args.no_cpu_baseline:
+            import oracle_lib as orc
+
+            ovm = orc.VoxelMap(RESOLUTION)
+            ovm.insert(orc.Cloud(tp, tc))
+            of = orc.Factor(ovm, orc.Cloud(sp, sc), num_threads=cpu_threads(orc))
+            ref = of.linearize_raw(poses[-1])
+            h_chk = np.zeros((1, capi.B2_LINEARIZED_DOUBLES))
+            capi.check(L.b2_factor_set_linearize(sset.set.h, poses_p[-1], h_chk.ctypes.data_as(dp)))
+            corr_equal = bool(np.array_equal(factor.correspondences(), of.correspondences()))
+            rel = float(np.abs(h_chk[0, :121] - ref[:121]).max() / np.abs(ref[:121]).max())
+            parity = {"checked_against": "CPU oracle, same cloud and pose", "correspondences_identical": corr_equal, "inliers": int(h_chk[0, 121]),
+                      "oracle_inliers": int(ref[121]), "max_rel_err_H_b_error": rel}
+            assert corr_equal and int(h_chk[0, 121]) == int(ref[121]) and rel < 1e-9, parity
 
         # ---- end-to-end arm: the public host entry point with HOST buffers (poses in, H/b records out) ----
         # N = 1: the C-ABI call itself (b2_factor_set_linearize), which is what NonlinearFactorSetGPU.linearize and the C++
-        #        adapters issue; N > 1: ShardedFactorSet.linearize (host poses -> kernel -> all-reduce -> host records).
+        #        adapters issue; N > 1: ShardedFactorSet.linearize (host poses -> kernel + exchange -> host records).
         h_out = np.zeros((1, capi.B2_LINEARIZED_DOUBLES))
-
-        linearize_host = capi.lib().b2_factor_set_linearize
+        linearize_host = L.b2_factor_set_linearize
         h_out_p = h_out.ctypes.data_as(dp)
 
         def e2e_step(pose, pose_p):
@@ -422,8 +443,7 @@ def run_gpu(args):
         barrier()
         e2e_s = 0.0
         for i in range(K):
-            if not args.no_flush:
-                flush_l2(i)
+            flush_l2(i)
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
@@ -431,15 +451,65 @@ def run_gpu(args):
             t0 = time.perf_counter()
             out = e2e_step(poses_c[W + i], poses_p[W + i])
             e2e_s += time.perf_counter() - t0
-        e2e_inliers = int(out[rank if world > 1 else 0, 121])
         barrier()
         clocks = sampler.stop() if rank == 0 else None
+        e2e_ms = max_over_ranks(e2e_s * 1e3)
 
-    # max over ranks
-    tt = torch.tensor([dev_total_ms, e2e_s * 1e3, float(kern_ms.mean())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_total_ms, e2e_ms, kern_ms_mean = [float(x) for x in tt.cpu()]
+        # ================= sub-record: STRONG scaling -- the same 1M-point factor split over the ranks =================
+        # every rank holds the whole target map and a contiguous 1/N slice of rank 0's source cloud; the N partial records are
+        # exchanged like any other records and summed (H, b and the error are sums over points)
+        strong = None
+        if world > 1 and not args.no_extra:
+            tp0, tc0, sp0, sc0 = make_inputs(0)
+            vm0 = g.GaussianVoxelMapGPU(RESOLUTION, ctx)
+            vm0.insert(g.PointCloud(tp0, tc0, ctx=ctx, flags=capi.B2_CLOUD_NO_REORDER))
+            lo, hi = rank * N_SOURCE // world, (rank + 1) * N_SOURCE // world
+            part = g.IntegratedVGICPFactor(0, 1, vm0, g.PointCloud(sp0[lo:hi], sc0[lo:hi], ctx=ctx), ctx=ctx)
+            ss = ShardedFactorSet([part], [rank], world, ctx=ctx)
+            poses0 = [np.ascontiguousarray(p.reshape(1, 16)) for p in make_poses(0, K + W)]
+            total = {}
+
+            def strong_step(pose):
+                total["rec"] = ss.linearize_device(pose).sum(0)  # the factor's H, b, error = sum of the ranks' partial records
+
+            ms_total, _ = time_steps(strong_step, poses0, W, K)
+            strong = {"workload": "ONE 1M-pt VGICP factor, source points split over the ranks, partial H/b records summed", "scaling": "strong",
+                      "ms_per_step": ms_total / K, "value": N_SOURCE * K / (ms_total * 1e-3), "unit": UNIT, "inliers": int(total["rec"][121].item())}
+            del ss, part, vm0
+
+        # ================= sub-record: cfg4 share -- 32 factors x 200k points per GPU in ONE set (256 factors at 8 GPUs) =================
+        cfg4 = None
+        if not args.no_extra:
+            F4, N4 = 32, 200_000
+            from gtsam_points_b200 import synthetic as syn
+
+            t0 = time.perf_counter()
+            fs, keep = [], []
+            for i in range(F4):
+                gid = rank * F4 + i
+                tpi, tci = syn.make_cloud(N4, stream=2 * gid + 1, scene_seed=2000 + gid // 4)
+                spi, sci = syn.make_cloud(N4, stream=2 * gid + 2, scene_seed=2000 + gid // 4)
+                vmi = g.GaussianVoxelMapGPU(RESOLUTION, ctx)
+                vmi.insert(g.PointCloud(tpi, tci, ctx=ctx, flags=capi.B2_CLOUD_NO_REORDER))
+                fs.append(g.IntegratedVGICPFactor(2 * gid, 2 * gid + 1, vmi, g.PointCloud(spi, sci, ctx=ctx), ctx=ctx))
+                keep.append(vmi)
+            setup4_s = time.perf_counter() - t0
+            s4 = ShardedFactorSet(fs, list(range(rank * F4, (rank + 1) * F4)), world * F4, ctx=ctx)
+            rng4 = np.random.default_rng(4000 + rank)
+            poses4 = [np.ascontiguousarray(np.stack([syn.random_pose(rng4, POSE_ROT, POSE_TRANS) for _ in range(F4)]).reshape(F4, 16)) for _ in range(K + W)]
+            if world == 1:
+                issue = L.b2_factor_set_issue_linearize
+
+                def cfg4_step(pose):
+                    capi.check(issue(s4.set.h, pose.ctypes.data_as(dp), s4.d_all.data_ptr()))
+            else:
+                def cfg4_step(pose):
+                    s4.linearize_device(pose)
+            ms_total, _ = time_steps(cfg4_step, poses4, W, K)
+            rec4 = s4.d_all.cpu().numpy()
+            cfg4 = {"workload": f"ISAM2-style relinearize: {F4} VGICP factors x {N4} points per GPU in ONE launch ({world * F4} factors sharded over {world} GPU(s)), records exchanged",
+                    "scaling": "weak", "factors_per_gpu": F4, "points_per_factor": N4, "ms_per_step": ms_total / K, "value": world * F4 * N4 * K / (ms_total * 1e-3), "unit": UNIT,
+                    "hit_rate": float(rec4[:, 121].sum() / (world * F4 * N4)), "setup_s": setup4_s}
 
     if rank == 0:
         value = world * N_SOURCE * K / (dev_total_ms * 1e-3)
@@ -493,6 +563,8 @@ def run_gpu(args):
                 "source_storage": {"point_bytes": int(cinfo.point_bytes), "cov_bytes": int(cinfo.cov_bytes), "morton_ordered": bool(cinfo.reordered)},
                 "l2_flush": not args.no_flush,
                 "setup_s": setup_s,
+                "parity_check": parity,
+                "e2e_minus_kernel_us": 1e3 * (e2e_ms / K - kern_ms_mean),
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * 1, "d2h_bytes_per_step": 1024 * world, "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches_dev),
@@ -503,7 +575,7 @@ def run_gpu(args):
                 "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": ncu_traffic(),
-                "kernel": "b2::factor_kernel<float,double,VGICP,LINEARIZE>",
+                "kernel": "b2::v2::factor_kernel<float,double,VGICP,LINEARIZE,SINGLE>",
                 "kernel_ms": kern_ms_mean,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_formula": "N*48 + N_buckets_ref*16 + V*52 + 992 with N_buckets_ref = 2^ceil(log2(2V)) (>= 16384)",
@@ -511,6 +583,7 @@ def run_gpu(args):
             },
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
+            "extra": {"strong_scaling_1m_factor": strong, "cfg4_share": cfg4},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -524,6 +597,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-records (strong-scaling split, cfg4 share): headline numbers only")
     ap.add_argument("--no-native", action="store_true", help="reference arm: skip the secondary -march=native measurement")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps (NOT a valid bench number)")
     args = ap.parse_args()

@@ -10,6 +10,8 @@ from .capi import B2Error  # noqa: F401
 from .factors import (  # noqa: F401
     HessianFactor,
     IntegratedGICPFactor,
+    IntegratedICPFactor,
+    IntegratedPointToPlaneICPFactor,
     IntegratedMatchingCostFactor,
     IntegratedVGICPFactor,
     IntegratedVGICPFactorGPU,

@@ -32,12 +32,17 @@ __device__ __forceinline__ VoxelBucket load_bucket(const VoxelBucket* p) {
   return b;
 }
 
-// Bucket groups: the table is an array of 64-byte groups of kGroup = 4 buckets; a key hashes to a group and is stored
-// in the first group of its (linear, over groups) probe sequence that had a free slot at insertion time.  Buckets are
-// never deleted, so a lookup may stop at the first group that still has an empty slot.  The table is sized for a load
-// factor <= 0.25, which makes >98% of all lookups (hits AND misses) resolve with ONE round trip of four independent
-// 16-byte loads out of two 32-byte sectors -- on the GPU the probe chain is pure latency, so its length is what counts.
-constexpr int kGroup = 4;
+// Bucket groups: the table is an array of groups of kGroup 16-byte buckets (32 bytes = one sector for kGroup = 2); a key hashes
+// to a group and is stored in the first group of its (linear, over groups) probe sequence that had a free slot at insertion
+// time.  Buckets are never deleted, so a lookup may stop at the first group that still has an empty slot.  The table is sized
+// for a load factor <= 0.25: ~95 % of all lookups (hits AND misses) resolve inside the home group, i.e. with ONE access -- on
+// the GPU the probe chain is pure latency, so its length is what counts -- and the factor kernel can stage the home group of
+// every point asynchronously (32 bytes per point in flight); the few keys whose home group is full continue with ordinary
+// loads.  (Round 1 used 64-byte groups of 4: 98 % one-access lookups, but twice the bytes per probe in flight.)
+#ifndef B2_BUCKET_GROUP
+#define B2_BUCKET_GROUP 2
+#endif
+constexpr int kGroup = B2_BUCKET_GROUP;
 
 struct BucketGroup {
   int4 b[kGroup];

@@ -9,23 +9,23 @@
 //     PRODUCER warp (one lane) issues 1-D bulk copies (cp.async.bulk, one per plane and CTA tile of kTile = 512 points,
 //     2-4 KB each) into a multi-stage shared-memory ring, completion on `full` mbarriers (complete_tx::bytes); stages come
 //     back through `empty` mbarriers on which every probe warp arrives once.  The probe warps compute no stream address.
-//   * everything the arithmetic GATHERS per hit -- the target record (80 B) and the source covariance (6 values) -- is
-//     requested by the PROBE warp the moment it knows the hit, with cp.async (LDGSTS: no register, no scoreboard), straight
-//     into the hit's slot of the shared-memory ring, next to (R p, target id).  A tile's hits are published to the accumulate
-//     warp one tile later, when cp.async.wait_group says their operands have landed.  Misses are never fetched.
-//   * the ACCUMULATE warps therefore read nothing but shared memory: ten conflict-free LDS.128 per hit, then ~150 float64
-//     operations; no global access, no polling of memory latency.
+//   * the BUCKET GROUP of the hash probe (the data-dependent access that bounds the probe side) is requested by the probe
+//     warp kSB - 1 tiles ahead with cp.async (LDGSTS: no register, no scoreboard) into a small per-warp staging ring, next
+//     to the rotated point R p it belongs to; when the probe warp later matches the group it reads shared memory only.
+//     In-flight probes per SM = kP x kWarpPoints x (kSB - 1) without holding a single register for them.
+//   * what the arithmetic GATHERS per hit -- the target record (80 B) and the source covariance (6 values) -- is requested
+//     by the ACCUMULATE warp for batch k + 1 (cp.async into a private double buffer) while it computes batch k: the float64
+//     arithmetic reads nothing but shared memory.  Misses are never fetched.
 //   * the pose of single-factor launches is a by-value kernel parameter: DMUL / DFMA take it from uniform registers, and the
 //     kernel never touches host memory on its way in.
 // What stays on a scoreboard is the bucket group of the hash probe (data-dependent address), kPPL points per lane in flight.
 //
-// Ring protocol (one ring per probe warp, single producer / single consumer, monotonic 32-bit counters in shared memory):
-// `tail` (published with st.release after the operands of those items have landed), `head` (released by the accumulate warp
+// Ring protocol (one ring per probe warp, single producer / single consumer, monotonic 32-bit counters in shared memory,
+// 32-byte items (R p, stored position | target id)): `tail` (published with st.release), `head` (released by the accumulate warp
 // after it has read a batch), `done` / `ack` (factor-run hand-shake: batches never straddle factors).  The accumulate warp
 // takes batches of exactly 32 consecutive hits (the last batch of a run may be shorter), rings are drained in strict
 // rotation, cross-warp / cross-CTA sums run in slot order: results are bit-reproducible run to run.
-// Liveness: a probe warp that has to wait for ring space first publishes everything it has in flight; ring capacity >=
-// one batch + one warp tile then guarantees that either side can always move.  All waits are bounded (trap, never hang).
+// Liveness: ring capacity >= one batch + one warp tile guarantees that either side can always move.  All waits are bounded (trap, never hang).
 //
 // This file is included once per kernel configuration (no include guard); the includer defines B2_V2_NAMESPACE and the
 // B2_V2_* parameters (see b2_factors.cu).
@@ -42,13 +42,14 @@ constexpr int kWarpPoints = 32 * kPPL;   // contiguous source points per probe w
 constexpr int kTile = kP * kWarpPoints;  // source points per CTA tile
 constexpr int kRing = B2_V2_RING;        // items per ring (power of two)
 constexpr int kSX = B2_V2_XYZ_STAGES;    // coordinate stages (CTA tiles in flight ahead of the probe warps)
-constexpr int kFields = 10;              // 16-byte fields per ring item: (u0,u1) (u2,slot|id) | record 5 x | covariance 3 x
+constexpr int kSB = B2_V2_BUCKET_STAGES;  // bucket-group stages per probe warp (groups requested kSB - 1 tiles ahead)
+constexpr int kOperandFields = 8;        // 16-byte fields per gathered hit: record 5 x | covariance 3 x
 constexpr int kRingsPerConsumer = kP / kC;
 constexpr uint32_t kBatch = 32u;
 static_assert(kP % 4 == 0 && kC % 4 == 0, "setmaxnreg works on warpgroups of 4 warps");
 static_assert(kP % kC == 0, "every accumulate warp drains the same number of rings");
 static_assert((kRing & (kRing - 1)) == 0 && kRing >= 32 + kWarpPoints, "ring capacity: a batch the accumulate warp can take + a tile's hits");
-static_assert(kSX >= 2, "stage counts");
+static_assert(kSX >= 3 && kSB >= 2, "stage counts");
 // setmaxnreg moves registers inside the CTA's OWN pool (what the launch allocated: threads x the per-thread count the
 // launch bounds give); the SM's unallocated remainder is not available.  A split that asks for more deadlocks the
 // accumulate warps in USETMAXREG.TRY_ALLOC.
@@ -70,6 +71,13 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+// Publication of a ring counter WITHOUT a fence: `st.release` compiles to MEMBAR.ALL.CTA + ST, and that barrier also waits for
+// every cp.async (LDGSTS) this thread still has in flight -- the bucket groups / operands requested tiles ahead -- which puts
+// the full memory latency back on the critical path of every tile.  What has to be ordered here is shared-memory traffic of
+// ONE warp (the item stores / item loads of its lanes, then the counter store of lane 0 after __syncwarp()): the shared-memory
+// pipeline executes a warp's accesses in program order, and __syncwarp() orders the lanes, so a volatile store is enough.
+// (Round 1 measured the same for `head`; `done` / `ack`, once per factor run, keep release semantics.)
+__device__ __forceinline__ void st_publish(uint32_t* p, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 struct Backoff {
   unsigned ns, max_ns, polls;
   __device__ __forceinline__ explicit Backoff(unsigned first_ns, unsigned cap_ns) : ns(first_ns), max_ns(cap_ns), polls(0u) {}
@@ -139,13 +147,22 @@ struct XyzStage {
   static constexpr uint32_t kCorrOff = 3u * kPlane;
   static constexpr uint32_t kBytes = 3u * kPlane + (MODE == MODE_ERROR ? kTile * 4u : 0u);
 };
-constexpr uint32_t kFieldBytes = kRing * 16u;              // one field of every slot (structure of arrays: lane -> slot is conflict-free)
-constexpr uint32_t kRingBytes1 = kFields * kFieldBytes;    // 160 bytes per item
+constexpr uint32_t kRingBytes1 = 2u * kRing * 16u;                                      // ring: (u0,u1) | (u2, position|id), field-major
+constexpr uint32_t kStageFields = 2u + kGroup;                                          // bucket stage per point: (u0,u1) (u2,aux) | kGroup buckets
+constexpr uint32_t kBucketStageBytes = kStageFields * kWarpPoints * 16u;                // one tile of one probe warp, field-major
+constexpr uint32_t kOperandBufBytes = kOperandFields * 32u * 16u;                       // one batch of gathered operands, field-major
+// 8-byte coordinates double the stage: one stage less keeps the CTA inside the 227 KB of shared memory
+template <typename PT>
+struct XStages {
+  static constexpr uint32_t value = sizeof(PT) == 8 ? static_cast<uint32_t>(kSX - 1) : static_cast<uint32_t>(kSX);
+};
 template <typename PT, typename CT, int MODE>
 struct Layout {
   static constexpr uint32_t kXyzOff = 0u;
-  static constexpr uint32_t kRingOff = kSX * XyzStage<PT, MODE>::kBytes;
-  static constexpr uint32_t kTotal = kRingOff + kP * kRingBytes1;
+  static constexpr uint32_t kRingOff = XStages<PT>::value * XyzStage<PT, MODE>::kBytes;
+  static constexpr uint32_t kBktOff = kRingOff + kP * kRingBytes1;
+  static constexpr uint32_t kOpOff = kBktOff + kP * kSB * kBucketStageBytes;
+  static constexpr uint32_t kTotal = kOpOff + kC * 2u * kOperandBufBytes;
   static_assert(kRingOff % 128u == 0u, "stage alignment");
 };
 
@@ -278,6 +295,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
               const __grid_constant__ DoneSignal sig, const __grid_constant__ PoseArg pose, const uint32_t* __restrict__ /*frozen_flags: kd-tree factors only*/) {
   using L = Layout<PT, CT, MODE>;
   using XS = XyzStage<PT, MODE>;
+  constexpr uint32_t kSXp = XStages<PT>::value;  // coordinate stages of this instantiation
   __shared__ Shared sh;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
 
@@ -334,7 +352,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
 #else
     if (warp != kP + kC || lane != 0) return;
 #endif
-    uint32_t j = 0u;  // CTA tiles issued so far: stage = j % kSX, use count = j / kSX
+    uint32_t j = 0u;  // CTA tiles issued so far: stage = j % kSXp, use count = j / kSXp
     uint32_t tile = tile_lo;
 #ifdef B2_V2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -351,10 +369,10 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       for (; tile < run_end; tile++, j++) {
         const uint32_t base = pt * kTile;
         const uint32_t cnt = base >= n_pad ? 0u : min(static_cast<uint32_t>(kTile), n_pad - base);  // multiple of 32
-        const uint32_t s = j % kSX;
+        const uint32_t s = j % kSXp;
         {
           B2_T0(tw);
-          if (j >= static_cast<uint32_t>(kSX)) mbar_wait(&sh.empty_x[s], ((j / kSX) - 1u) & 1u);
+          if (j >= kSXp) mbar_wait(&sh.empty_x[s], ((j / kSXp) - 1u) & 1u);
           B2_TACC(0, tw);
         }
         fence_proxy_async();  // the stage was read through the generic proxy
@@ -381,13 +399,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     // ================================================= PROBE warps =================================================
     set_role_registers<B2_V2_REGS_PRODUCER>();
     const int p = warp;
-    const uint32_t ring_s = smem_u32(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
     double2* const ring = reinterpret_cast<double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
-    uint32_t tail = 0u;       // items written (operands requested)
-    uint32_t committed = 0u;  // tail at the previous tile's cp.async commit: those items' operands are the next to land
-    uint32_t published = 0u;  // tail the accumulate warp has been told about
-    uint32_t run = 0u;
-    uint32_t j = 0u;  // CTA tiles this warp has processed so far (all runs): stage = j % kSX, use count = j / kSX
+    unsigned char* const bkt = dyn_smem + L::kBktOff + static_cast<size_t>(p) * kSB * kBucketStageBytes;
+    const uint32_t bkt_s = smem_u32(bkt);
+    uint32_t tail = 0u, run = 0u;
+    uint32_t j = 0u;  // CTA tiles this warp has MATCHED so far (all runs): bucket stage = j % kSB; phase A runs kSB - 1 tiles ahead
     uint32_t head_seen = 0u;
     uint32_t tile = tile_lo;
 #ifdef B2_V2_TIMING
@@ -397,12 +413,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     while (tile < tile_hi) {
       const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
       const uint32_t n = dg->n;
-      const size_t n_pad = dg->n_pad;
       const uint32_t f_tile_begin = dg->tile_begin;
       const uint32_t run_end = min(tile_hi, f_tile_begin + dg->num_tiles);
       const uint32_t out_index = dg->out_index;
-      const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
-      const double* __restrict__ records = dg->records;
       int32_t* __restrict__ corr = dg->corr;
       const VoxelBucket* __restrict__ buckets = dg->buckets;
       const uint32_t bucket_mask = dg->bucket_mask;
@@ -424,128 +437,139 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       // Virtual tile v of the factor (the CTA owns a contiguous range of them) is physical tile (v * S) mod n_tiles with
       // S ~ 0.618 n_tiles coprime to n_tiles: every CTA samples the (Morton-ordered) cloud quasi-uniformly.
       const uint32_t f_num_tiles = dg->num_tiles, perm_stride = dg->perm_stride;
-      uint32_t pt_cur = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles);
-
-      // Per tile, two phases, software-pipelined one tile apart:
-      //   A(j + 1): read the tile's coordinates from the stage, rotate, floor, hash, start the bucket group of every point
-      //             towards L2 (prefetch: no register, no scoreboard), hand the stage back -- results stay in registers;
-      //   B(j):     load the (now L2-resident) bucket groups, match, store corr[], compact the hits into the ring and request
-      //             their operands.
-      struct Pre {
-        double u[kPPL][3];
-        int cx[kPPL], cy[kPPL], cz[kPPL], id[kPPL];
-        uint32_t grp_idx[kPPL];
-        bool ok[kPPL];
+      auto next_tile = [&](uint32_t pt) {
+        pt += perm_stride;
+        return pt >= f_num_tiles ? pt - f_num_tiles : pt;
       };
-      auto phase_a = [&](Pre& a, uint32_t jj, uint32_t pt) {
-        const uint32_t sx = jj % kSX;
+      const uint32_t K = run_end - tile;  // tiles of this run
+      uint32_t pt_a = static_cast<uint32_t>(static_cast<unsigned long long>(tile - f_tile_begin) * perm_stride % f_num_tiles), pt_b = pt_a;
+
+      // Phase A(jj): the tile's coordinates (TMA stage jj % kSXp) -> R p -> voxel coordinate -> hash; R p goes into bucket stage
+      // jj % kSB, the bucket group is requested into the same slot (cp.async), the coordinate stage goes back to the producer.
+      auto phase_a = [&](uint32_t jj) {
+        const uint32_t sx = jj % kSXp;
         {
           B2_T0(tw);
-          mbar_wait(&sh.full_x[sx], (jj / kSX) & 1u);
+          mbar_wait(&sh.full_x[sx], (jj / kSXp) & 1u);
           B2_TACC(1, tw);
         }
+        B2_T0(t_a);
         const unsigned char* xs = dyn_smem + L::kXyzOff + sx * XS::kBytes;
-        const uint32_t base = pt * kTile + p * kWarpPoints + lane;
+        double2* st = reinterpret_cast<double2*>(bkt + (jj % kSB) * kBucketStageBytes);
+        const uint32_t st_s = bkt_s + (jj % kSB) * kBucketStageBytes;
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
-          const int li = p * kWarpPoints + lane + 32 * q;
-          a.ok[q] = base + 32 * q < n;
+          const int lw = lane + 32 * q;             // position inside the warp tile
+          const int li = p * kWarpPoints + lw;      // position inside the CTA tile
           const double x = static_cast<double>(reinterpret_cast<const PT*>(xs)[li]);
           const double y = static_cast<double>(reinterpret_cast<const PT*>(xs + XS::kPlane)[li]);
           const double z = static_cast<double>(reinterpret_cast<const PT*>(xs + 2 * XS::kPlane)[li]);
-          a.id[q] = -1;
-          if (MODE == MODE_ERROR) a.id[q] = a.ok[q] ? reinterpret_cast<const int*>(xs + XS::kCorrOff)[li] : -1;
           // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
-          a.u[q][0] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
-          a.u[q][1] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
-          a.u[q][2] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
-          a.cx[q] = a.cy[q] = a.cz[q] = 0;
-          a.grp_idx[q] = 0u;
+          const double u0 = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
+          const double u1 = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
+          const double u2 = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
+          int aux = -1;
+          if (MODE == MODE_ERROR) aux = reinterpret_cast<const int*>(xs + XS::kCorrOff)[li];  // the frozen correspondence
+          st[lw] = make_double2(u0, u1);
+          st[kWarpPoints + lw] = make_double2(u2, __longlong_as_double(static_cast<long long>(aux)));
           if (MODE == MODE_LINEARIZE && KIND == 0) {
-            a.cx[q] = voxel_coord1(__dadd_rn(a.u[q][0], tv(0)), inv_leaf);
-            a.cy[q] = voxel_coord1(__dadd_rn(a.u[q][1], tv(1)), inv_leaf);
-            a.cz[q] = voxel_coord1(__dadd_rn(a.u[q][2], tv(2)), inv_leaf);
-            a.grp_idx[q] = voxel_hash(a.cx[q], a.cy[q], a.cz[q]) & bucket_mask;
-#if B2_V2_PREFETCH_GROUPS
-            const char* gp = reinterpret_cast<const char*>(buckets) + static_cast<size_t>(a.grp_idx[q]) * (kGroup * sizeof(VoxelBucket));
-            prefetch_l2(gp);
-            prefetch_l2(gp + 32);
+            const int cx = voxel_coord1(__dadd_rn(u0, tv(0)), inv_leaf);
+            const int cy = voxel_coord1(__dadd_rn(u1, tv(1)), inv_leaf);
+            const int cz = voxel_coord1(__dadd_rn(u2, tv(2)), inv_leaf);
+            const uint32_t g = voxel_hash(cx, cy, cz) & bucket_mask;
+#ifndef B2_V2_DEBUG_NO_PROBE
+            const VoxelBucket* gp = buckets + static_cast<size_t>(g) * kGroup;
+#pragma unroll
+            for (int k = 0; k < kGroup; k++) cp_async16(st_s + (2u + k) * (kWarpPoints * 16u) + lw * 16u, gp + k);
 #endif
           }
         }
+        cp_async_commit();
         // every lane has read its coordinates: the stage goes back to the producer (one arrival per probe warp)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_x[sx]);
+        B2_TACC(2, t_a);
       };
 
-      Pre cur;
-#if B2_V2_PIPELINE_A
-      Pre nxt;
-      phase_a(nxt, j, pt_cur);
-#endif
+      // prologue: kSB - 1 tiles ahead (empty commit groups keep the group count uniform for short runs)
 #pragma unroll 1
-      for (; tile < run_end; tile++, j++) {
-        B2_T0(t_work);
-#if B2_V2_PIPELINE_A
-        cur = nxt;
-#else
-        phase_a(cur, j, pt_cur);
-#endif
-        const uint32_t base = pt_cur * kTile + p * kWarpPoints + lane;
-        int id[kPPL];
-        BucketGroup grp[kPPL];
-#pragma unroll
-        for (int q = 0; q < kPPL; q++) {
-          id[q] = cur.id[q];
-#ifndef B2_V2_DEBUG_NO_PROBE
-          if (MODE == MODE_LINEARIZE && KIND == 0) grp[q] = load_group(buckets, cur.grp_idx[q]);
-#endif
+      for (uint32_t a = 0; a < static_cast<uint32_t>(kSB - 1); a++) {
+        if (a < K) {
+          phase_a(j + a);
+          pt_a = next_tile(pt_a);
+        } else {
+          cp_async_commit();
         }
-        pt_cur += perm_stride;
-        if (pt_cur >= f_num_tiles) pt_cur -= f_num_tiles;
-#if B2_V2_PIPELINE_A
-        if (tile + 1 < run_end) phase_a(nxt, j + 1, pt_cur);  // overlaps the bucket-group loads above
-#endif
+      }
+
+#pragma unroll 1
+      for (uint32_t k = 0; k < K; k++, tile++, j++) {
+        if (k + kSB - 1 < K) {
+          phase_a(j + kSB - 1);
+          pt_a = next_tile(pt_a);
+        } else {
+          cp_async_commit();
+        }
+        // ---- Phase B(j): the tile whose bucket groups were requested kSB - 1 tiles ago ----
+        {
+          B2_T0(tw);
+          cp_async_wait<kSB - 1>();  // all but the newest kSB - 1 groups have landed: this lane's own requests of tile j included
+          B2_TACC(4, tw);
+        }
+        B2_T0(t_b);
+        const double2* st = reinterpret_cast<const double2*>(bkt + (j % kSB) * kBucketStageBytes);
+        const uint32_t base = pt_b * kTile + p * kWarpPoints + lane;
+        pt_b = next_tile(pt_b);
+        double u[kPPL][3];
+        int id[kPPL];
+        bool ok[kPPL];
         uint32_t mask[kPPL], cnt = 0u;
 #pragma unroll
         for (int q = 0; q < kPPL; q++) {
+          const int lw = lane + 32 * q;
+          ok[q] = base + 32 * q < n;
+          const double2 q0 = st[lw], q1 = st[kWarpPoints + lw];
+          u[q][0] = q0.x, u[q][1] = q0.y, u[q][2] = q1.x;
+          id[q] = -1;
+          if (MODE == MODE_ERROR) id[q] = ok[q] ? static_cast<int>(__double_as_longlong(q1.y)) : -1;
           if (MODE == MODE_LINEARIZE) {
             if (KIND == 0) {
+              // the same individually rounded operations as phase A: identical voxel coordinate
+              const int cx = voxel_coord1(__dadd_rn(u[q][0], tv(0)), inv_leaf);
+              const int cy = voxel_coord1(__dadd_rn(u[q][1], tv(1)), inv_leaf);
+              const int cz = voxel_coord1(__dadd_rn(u[q][2], tv(2)), inv_leaf);
 #ifdef B2_V2_DEBUG_NO_PROBE
-              id[q] = static_cast<int>(cur.grp_idx[q] & 0xffffu);  // measurement aid: no table access, every point "hits" some record
+              id[q] = static_cast<int>((voxel_hash(cx, cy, cz) & bucket_mask) & 0xffffu);  // measurement aid: no table access, every point "hits" some record
 #else
-              id[q] = match_group(grp[q], cur.cx[q], cur.cy[q], cur.cz[q]);
-#endif
-              uint32_t g = cur.grp_idx[q];
-              while (id[q] == -2) {  // rare (<2% at load <= 0.25): the home group is full, walk on
-                g = (g + 1) & bucket_mask;
-                id[q] = match_group(load_group(buckets, g), cur.cx[q], cur.cy[q], cur.cz[q]);
+              BucketGroup grp;
+#pragma unroll
+              for (int k = 0; k < kGroup; k++) grp.b[k] = reinterpret_cast<const int4*>(st)[(2 + k) * kWarpPoints + lw];
+              id[q] = match_group(grp, cx, cy, cz);
+              if (id[q] == -2) {  // rare: the home group is full and does not hold the key -- walk on (synchronous loads)
+                uint32_t g = voxel_hash(cx, cy, cz) & bucket_mask;
+                do {
+                  g = (g + 1) & bucket_mask;
+                  id[q] = match_group(load_group(buckets, g), cx, cy, cz);
+                } while (id[q] == -2);
               }
+#endif
             } else {
               double sq;
-              id[q] = kdtree_nn1_warp(tview, __dadd_rn(cur.u[q][0], tv(0)), __dadd_rn(cur.u[q][1], tv(1)), __dadd_rn(cur.u[q][2], tv(2)), cur.ok[q], max_sq, &sq);
+              id[q] = kdtree_nn1_warp(tview, __dadd_rn(u[q][0], tv(0)), __dadd_rn(u[q][1], tv(1)), __dadd_rn(u[q][2], tv(2)), ok[q], max_sq, &sq);
             }
-            if (cur.ok[q]) corr[base + 32 * q] = id[q];
+            if (ok[q]) corr[base + 32 * q] = id[q];
           }
-          mask[q] = __ballot_sync(0xffffffffu, cur.ok[q] && id[q] >= 0);
+          mask[q] = __ballot_sync(0xffffffffu, ok[q] && id[q] >= 0);
           cnt += __popc(mask[q]);
         }
-        B2_TACC(2, t_work);
-        B2_T0(t_ring);
-        // The PREVIOUS tile's operands were requested a whole tile ago: wait for them and publish its hits -- BEFORE this
-        // tile's requests are issued, so that the release fence below has no copy of its own in flight to wait for.
-        cp_async_wait<0>();
-        if (committed != published) {
-          __syncwarp();
-          if (lane == 0) st_release(&sh.tail[p], committed);
-          published = committed;
-        }
+        B2_TACC(5, t_b);
         if (cnt != 0u) {
-          // room in the ring (everything written so far is published: the accumulate warp can always move)
+          B2_T0(t_ring);
+          // room in the ring
           if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
             head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
             if (tail + cnt - head_seen > static_cast<uint32_t>(kRing)) {
-              Backoff bo(32u, 256u);
+              Backoff bo(B2_V2_BACKOFF_MIN, B2_V2_BACKOFF_MAX);
               do {
                 bo.wait();
                 head_seen = __shfl_sync(0xffffffffu, ld_acquire(&sh.head[p]), 0);
@@ -556,52 +580,33 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           for (int q = 0; q < kPPL; q++) {
             if ((mask[q] >> lane) & 1u) {
               const uint32_t slot = (tail + __popc(mask[q] & ((1u << lane) - 1u))) & (kRing - 1);
-              const unsigned long long bits = static_cast<unsigned long long>(slot) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
-              ring[slot] = make_double2(cur.u[q][0], cur.u[q][1]);
-              ring[kRing + slot] = make_double2(cur.u[q][2], __longlong_as_double(static_cast<long long>(bits)));
-              // operands of this hit, requested now, landed before the hit is published: target record (5 x 16 B) ...
-              const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(id[q]) * kRecordDoubles);
-              const uint32_t dst = ring_s + 2u * kFieldBytes + slot * 16u;
-#pragma unroll
-              for (int k = 0; k < 5; k++) cp_async16(dst + k * kFieldBytes, rec + 16 * k);
-              // ... and the source covariance (6 planes): (a00, a01) (a02, a11) (a12, a22), one 8-byte cell each
-              const CT* cp = cv + (base + 32 * q);
-              const uint32_t dc = ring_s + 7u * kFieldBytes + slot * 16u;
-#pragma unroll
-              for (int k = 0; k < 6; k++) cp_async_small<static_cast<int>(sizeof(CT))>(dc + (k >> 1) * kFieldBytes + (k & 1) * 8u, cp + static_cast<size_t>(k) * n_pad);
+              const unsigned long long bits = static_cast<unsigned long long>(base + 32 * q) | (static_cast<unsigned long long>(static_cast<uint32_t>(id[q])) << 32);
+              ring[slot] = make_double2(u[q][0], u[q][1]);
+              ring[kRing + slot] = make_double2(u[q][2], __longlong_as_double(static_cast<long long>(bits)));
             }
             tail += __popc(mask[q]);
           }
+          __syncwarp();
+          if (lane == 0) st_publish(&sh.tail[p], tail);
+          B2_TACC(3, t_ring);
         }
-        cp_async_commit();
-        committed = tail;
-        B2_TACC(3, t_ring);
       }
-      // end of this CTA's run of the factor: everything lands, is published, then wait until the accumulate warp has drained the ring
+      // end of this CTA's run of the factor: publish, then wait until the accumulate warp has drained the ring
       cp_async_wait<0>();
       run++;
       __syncwarp();
-      if (lane == 0) {
-        st_release(&sh.tail[p], tail);
-        st_release(&sh.done[p], run);
-      }
-      committed = published = tail;
+      if (lane == 0) st_release(&sh.done[p], run);
       {
         B2_T0(tw);
         Backoff bo(128u, 512u);
         while (ld_acquire(&sh.ack[p]) != run) bo.wait();
-        B2_TACC(5, tw);
+        B2_TACC(6, tw);
       }
       head_seen = tail;
       __syncwarp();
     }
 #ifdef B2_V2_TIMING
     tacc[7] = clock64() - t_begin;
-    {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      tacc[6] = smid;
-    }
     if (lane == 0)
       for (int k = 0; k < 8; k++) g_warp_cycles[(blockIdx.x * 32 + warp) * 8 + k] = tacc[k];
 #endif
@@ -610,7 +615,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     set_role_registers<B2_V2_REGS_CONSUMER>();
     const int cw = warp - kP;        // accumulate warp index
     const int ctid = tid - kP * 32;  // thread index within the accumulate group
-    uint32_t head[kRingsPerConsumer];  // items taken from each of this warp's rings
+    unsigned char* const opbuf = dyn_smem + L::kOpOff + static_cast<size_t>(cw) * 2u * kOperandBufBytes;
+    const uint32_t opbuf_s = smem_u32(opbuf);
+    uint32_t head[kRingsPerConsumer];  // items taken (fetched) from each of this warp's rings
 #pragma unroll
     for (int r = 0; r < kRingsPerConsumer; r++) head[r] = 0u;
     uint32_t run = 0u;
@@ -655,13 +662,23 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const uint32_t run_end = min(tile_hi, d.tile_begin + d.num_tiles);
       run++;
 
-      // Strict rotation over this warp's rings, in batches of 32 consecutive items (always full except for a probe warp's
-      // last batch of the run).  Every operand is in the ring item: ten 16-byte fields, lane -> slot, conflict-free.
+      // One batch = up to 32 consecutive hits of one ring (always 32 except for a probe warp's last batch of the run).
+      // `cur` is being computed, `nxt` has been fetched: its gathered operands -- target record (5 x 16 B) and source
+      // covariance (6 cells of 8 B) per hit -- are on their way into the other half of this warp's operand buffer (cp.async:
+      // no register, no scoreboard).  Strict rotation over the warp's rings keeps the batch sequence a function of the data.
+      const double* __restrict__ records = d.records;
+      const CT* __restrict__ cv = static_cast<const CT*>(d.covs);
+      const size_t n_pad = d.n_pad;
+      struct Bat {
+        uint32_t hd, nb;
+        int r;
+        bool fin, valid;
+      };
       constexpr uint32_t kAllFinished = (1u << kRingsPerConsumer) - 1u;
-      uint32_t finished = 0u;
-      int r = 0;
-      while (finished != kAllFinished) {
-        while (finished & (1u << r)) r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+      uint32_t finished = 0u;  // rings whose final batch of this run has been FETCHED
+      int rot = 0;             // next ring in the strict rotation
+      uint32_t buf = 0u;
+      auto fetch = [&](int r, bool blocking, Bat& bt, uint32_t which) -> bool {
         const int p = cw + r * kC;
         uint32_t hd = 0u;
 #pragma unroll
@@ -669,69 +686,120 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           if (k == r) hd = head[k];
         uint32_t nb = 0u;
         bool fin = false;
-        {
-          B2_T0(tw);
-          Backoff bo(32u, 128u);
-          while (true) {
-            const uint32_t dn = ld_acquire(&sh.done[p]);
-            const uint32_t tl = ld_acquire(&sh.tail[p]);
-            const uint32_t avail = tl - hd;
-            if (avail >= kBatch) {
-              nb = kBatch;
-              break;
-            }
-            if (dn == run) {  // the probe warp finished this run: `tl` is final
-              nb = avail;
-              fin = true;
-              break;
-            }
-            bo.wait();
+        Backoff bo(B2_V2_BACKOFF_MIN, B2_V2_BACKOFF_MAX);
+        while (true) {
+          const uint32_t dn = ld_acquire(&sh.done[p]);
+          const uint32_t tl = ld_acquire(&sh.tail[p]);
+          const uint32_t avail = tl - hd;
+          if (avail >= kBatch) {
+            nb = kBatch;
+            break;
           }
-          B2_TACC(0, tw);
+          if (dn == run) {  // the probe warp finished this run: `tl` is final
+            nb = avail;
+            fin = true;
+            break;
+          }
+          if (!blocking) return false;
+          bo.wait();
         }
-        B2_T0(t_comp);
-#ifdef B2_V2_TIMING
-        tacc[5]++;
-#endif
-        const bool valid = static_cast<uint32_t>(lane) < nb;
-        if (valid) {  // uniform for full batches
-          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1) + ((hd + lane) & (kRing - 1));
-          const double2 q0 = rg[0], q1 = rg[kRing];
-#ifndef B2_V2_DEBUG_NO_ACCUM
-          TargetRec T;
-          T.r01 = rg[2 * kRing];
-          T.r23 = rg[3 * kRing];
-          T.r45 = rg[4 * kRing];
-          T.r67 = rg[5 * kRing];
-          T.r89 = rg[6 * kRing];
-          const double2 c0 = rg[7 * kRing], c1 = rg[8 * kRing], c2 = rg[9 * kRing];
-          auto cell = [](double v) -> double {  // an 8-byte cell holds a double, or a float in its low half
-            return sizeof(CT) == 8 ? v : static_cast<double>(__int_as_float(__double2loint(v)));
-          };
-          SourceCov A;
-          A.a00 = cell(c0.x);
-          A.a01 = cell(c0.y);
-          A.a02 = cell(c1.x);
-          A.a11 = cell(c1.y);
-          A.a12 = cell(c2.x);
-          A.a22 = cell(c2.y);
-          accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
-#else
-          acc[28] += q0.x * 0.0 + 1.0 + q1.x * 0.0;  // measurement aid: probe-side throughput only
-#endif
-        }
-        // operands read: hand the ring slots back to the probe warp
-        __syncwarp();
-        if (lane == 0) {
-          st_release(&sh.head[p], hd + nb);
-          if (fin) st_release(&sh.ack[p], run);
-        }
+        bt.hd = hd, bt.nb = nb, bt.r = r, bt.fin = fin, bt.valid = true;
 #pragma unroll
         for (int k = 0; k < kRingsPerConsumer; k++)
           if (k == r) head[k] = hd + nb;
         if (fin) finished |= 1u << r;
-        r = (r + 1 == kRingsPerConsumer) ? 0 : r + 1;
+        if (static_cast<uint32_t>(lane) < nb) {
+          const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1);
+          const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(rg[kRing + ((hd + lane) & (kRing - 1))].y));
+          const char* rec = reinterpret_cast<const char*>(records + static_cast<size_t>(bits >> 32) * kRecordDoubles);
+          const CT* cp = cv + static_cast<uint32_t>(bits);
+          const uint32_t dst = opbuf_s + which * kOperandBufBytes + lane * 16u;
+#pragma unroll
+          for (int k = 0; k < 5; k++) cp_async16(dst + k * 512u, rec + 16 * k);
+#pragma unroll
+          for (int k = 0; k < 6; k++) cp_async_small<static_cast<int>(sizeof(CT))>(dst + (5u + (k >> 1)) * 512u + (k & 1) * 8u, cp + static_cast<size_t>(k) * n_pad);
+        }
+        cp_async_commit();
+        return true;
+      };
+      auto next_ring = [&](int from) -> int {  // first unfinished ring at or after `from` in the rotation (-1: none)
+#pragma unroll
+        for (int k = 0; k < kRingsPerConsumer; k++) {
+          const int r = (from + k) % kRingsPerConsumer;
+          if (!(finished & (1u << r))) return r;
+        }
+        return -1;
+      };
+
+      Bat cur{0u, 0u, 0, false, false}, nxt{0u, 0u, 0, false, false};
+      while (true) {
+        if (!cur.valid) {
+          const int r = next_ring(rot);
+          if (r < 0) break;
+          B2_T0(tw);
+          fetch(r, true, cur, buf);
+          B2_TACC(0, tw);
+          rot = (r + 1) % kRingsPerConsumer;
+        }
+        // get the following batch on its way before computing this one
+        nxt.valid = false;
+        {
+          const int r = next_ring(rot);
+          if (r >= 0 && fetch(r, false, nxt, buf ^ 1u)) rot = (r + 1) % kRingsPerConsumer;
+        }
+        {
+          B2_T0(t_cp);
+          if (nxt.valid)
+            cp_async_wait<1>();
+          else
+            cp_async_wait<0>();
+          B2_TACC(1, t_cp);
+        }
+        B2_T0(t_comp);
+#ifdef B2_V2_TIMING
+        tacc[5]++;
+        if (nxt.valid) tacc[4]++;
+#endif
+        {
+          const int p = cw + cur.r * kC;
+          const bool valid = static_cast<uint32_t>(lane) < cur.nb;
+          if (valid) {  // uniform for full batches
+            const double2* rg = reinterpret_cast<const double2*>(dyn_smem + L::kRingOff + static_cast<size_t>(p) * kRingBytes1) + ((cur.hd + lane) & (kRing - 1));
+            const double2 q0 = rg[0], q1 = rg[kRing];
+#ifndef B2_V2_DEBUG_NO_ACCUM
+            const double2* ob = reinterpret_cast<const double2*>(opbuf + buf * kOperandBufBytes) + lane;
+            TargetRec T;
+            T.r01 = ob[0];
+            T.r23 = ob[32];
+            T.r45 = ob[64];
+            T.r67 = ob[96];
+            T.r89 = ob[128];
+            const double2 c0 = ob[160], c1 = ob[192], c2 = ob[224];
+            auto cell = [](double v) -> double {  // an 8-byte cell holds a double, or a float in its low half
+              return sizeof(CT) == 8 ? v : static_cast<double>(__int_as_float(__double2loint(v)));
+            };
+            SourceCov A;
+            A.a00 = cell(c0.x);
+            A.a01 = cell(c0.y);
+            A.a02 = cell(c1.x);
+            A.a11 = cell(c1.y);
+            A.a12 = cell(c2.x);
+            A.a22 = cell(c2.y);
+            accumulate_point_f<MODE>(acc, rl, tt, q0.x, q0.y, q1.x, T, A);
+#else
+            acc[28] += q0.x * 0.0 + 1.0 + q1.x * 0.0;  // measurement aid: probe-side throughput only
+#endif
+          }
+          // ring slots read: hand them back to the probe warp
+          __syncwarp();
+          if (lane == 0) {
+            st_publish(&sh.head[p], cur.hd + cur.nb);
+            if (cur.fin) st_release(&sh.ack[p], run);
+          }
+        }
         B2_TACC(2, t_comp);
+        cur = nxt;
+        buf ^= 1u;
       }
       B2_T0(t_fl);
       flush_factor<MODE>(sh, acc, ctid, partials, counters, out, pe, sig);

@@ -110,7 +110,7 @@ __host__ __device__ __forceinline__ uint32_t cta_tile_begin(uint32_t c, uint32_t
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int ctid, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-                                             const double* __restrict__ poses_lin, const DoneSignal& sig) {
+                                             const double* __restrict__ pose_lin /* this factor's linearization pose (16 doubles) */, const DoneSignal& sig) {
   constexpr int kCT = kC * 32;
   const int lane = ctid & 31, warp = ctid >> 5;
   const double w = warp_reduce32(v, lane);
@@ -165,7 +165,7 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
   epilogue_store(rec, sh.A, sh.X, sh.D, sh.tot, ctid);
   if (ctid >= 100 && ctid < 116) {
     // remember the linearization point with the factor (error-only launches of ANY set read it back)
-    d.lin_pose[ctid - 100] = __ldg(poses_lin + static_cast<size_t>(d.out_index) * 16 + (ctid - 100));
+    d.lin_pose[ctid - 100] = pose_lin[ctid - 100];
   }
   __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
   consumer_barrier();
@@ -208,20 +208,30 @@ __device__ __forceinline__ void load_meta(Batch& b, const double2* __restrict__ 
   b.id = b.valid ? static_cast<int>(bits >> 32) : 0;
 }
 
-template <typename CT>
+// KIND: 0 VGICP, 1 GICP, 2 point-to-point ICP, 3 point-to-plane ICP (kd-tree search for 1..3; ICP factors carry no source covariance)
+template <typename CT, int KIND>
 __device__ __forceinline__ void load_operands(Batch& b, const double* __restrict__ records, const CT* __restrict__ cv, size_t n_pad) {
   b.T = load_record(records, b.id);
-  b.A = load_cov(cv, n_pad, b.i);
+  if (KIND <= 1)
+    b.A = load_cov(cv, n_pad, b.i);
+  else
+    b.A = SourceCov{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 }
+template <int KIND>
+struct MetricOf {
+  static constexpr int value = KIND <= 1 ? 0 : KIND - 1;
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel.  KIND: 0 = VGICP (voxel hash probe), 1 = GICP (kd-tree 1-NN).  MODE: linearize / error-only.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename PT, typename CT, int KIND, int MODE>
+// SINGLE: the launch covers exactly one factor and its pose is the by-value parameter `pose` (linearize: the linearization
+// point; error: the evaluation point) -- DMUL / DFMA take it from uniform registers, nothing is read from host memory.
+template <typename PT, typename CT, int KIND, int MODE, bool SINGLE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__ tile_factor, uint32_t num_tiles, const double* __restrict__ poses_lin,
               const double* __restrict__ poses_eval, double* __restrict__ partials, unsigned int* __restrict__ counters, double* __restrict__ out,
-              const DoneSignal sig, const PoseArg /*pose: by-value poses are a feature of the v2 kernel*/, const uint32_t* __restrict__ frozen_flags) {
+              const __grid_constant__ DoneSignal sig, const __grid_constant__ PoseArg pose, const uint32_t* __restrict__ frozen_flags) {
   __shared__ Shared sh;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double2* const rings = reinterpret_cast<double2*>(dyn_smem);
@@ -250,7 +260,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     uint32_t tail = 0u, run = 0u;
     uint32_t tile = tile_lo;
     while (tile < tile_hi) {
-      const FactorDesc* __restrict__ dg = descs + __ldg(tile_factor + tile);
+      const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
       const uint32_t n = dg->n;
       const size_t n_pad = dg->n_pad;
       const uint32_t f_tile_begin = dg->tile_begin;
@@ -268,14 +278,16 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const double inv_leaf = dg->inv_leaf;
       // Residuals / correspondences are evaluated at this pose (linearize: the linearization point itself).  It lives in
       // this warp's shared-memory slot, not in registers: 24 registers less per probe thread, re-read (broadcast) per tile.
-      __syncwarp();
-      if (lane < 12) {
-        const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(out_index) * 16;
-        sh.probe_pose[p][lane] = __ldg(pe + (lane < 9 ? (lane / 3) * 4 + lane % 3 : (lane - 9) * 4 + 3));
+      if (!SINGLE) {
+        __syncwarp();
+        if (lane < 12) {
+          const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(out_index) * 16;
+          sh.probe_pose[p][lane] = __ldg(pe + (lane < 9 ? (lane / 3) * 4 + lane % 3 : (lane - 9) * 4 + 3));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      const double(&R)[9] = *reinterpret_cast<const double(*)[9]>(&sh.probe_pose[p][0]);
-      const double(&t)[3] = *reinterpret_cast<const double(*)[3]>(&sh.probe_pose[p][9]);
+      auto Rm = [&](int i) -> double { return SINGLE ? pose.m[(i / 3) * 4 + (i % 3)] : sh.probe_pose[p][i]; };
+      auto tvec = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : sh.probe_pose[p][9 + i]; };
       const KdTreeView tv{dg->nodes, dg->leaf_pts, static_cast<int>(dg->leaf_f32)};
       const double max_sq = dg->max_sq;
 
@@ -348,11 +360,17 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         for (int k = 0; k < kPPL; k++) {
           ok[k] = base + k * 32 < n;
           id[k] = (frozen && ok[k]) ? c.cid[k] : -1;
-          rotate_point(R, static_cast<double>(c.x[k]), static_cast<double>(c.y[k]), static_cast<double>(c.z[k]), u[k][0], u[k][1], u[k][2]);
+          {
+            // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
+            const double x = static_cast<double>(c.x[k]), y = static_cast<double>(c.y[k]), z = static_cast<double>(c.z[k]);
+            u[k][0] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(0), x), __dmul_rn(Rm(1), y)), __dmul_rn(Rm(2), z));
+            u[k][1] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(3), x), __dmul_rn(Rm(4), y)), __dmul_rn(Rm(5), z));
+            u[k][2] = __dadd_rn(__dadd_rn(__dmul_rn(Rm(6), x), __dmul_rn(Rm(7), y)), __dmul_rn(Rm(8), z));
+          }
           if (MODE == MODE_LINEARIZE && KIND == 0 && !frozen) {
-            cx[k] = voxel_coord1(__dadd_rn(u[k][0], t[0]), inv_leaf);
-            cy[k] = voxel_coord1(__dadd_rn(u[k][1], t[1]), inv_leaf);
-            cz[k] = voxel_coord1(__dadd_rn(u[k][2], t[2]), inv_leaf);
+            cx[k] = voxel_coord1(__dadd_rn(u[k][0], tvec(0)), inv_leaf);
+            cy[k] = voxel_coord1(__dadd_rn(u[k][1], tvec(1)), inv_leaf);
+            cz[k] = voxel_coord1(__dadd_rn(u[k][2], tvec(2)), inv_leaf);
             grp_idx[k] = voxel_hash(cx[k], cy[k], cz[k]) & bucket_mask;
 #ifndef B2_WS_DEBUG_NO_PROBE
             grp[k] = load_group(buckets, grp_idx[k]);
@@ -376,7 +394,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
               }
             } else {
               double sq;
-              id[k] = kdtree_nn1_warp(tv, __dadd_rn(u[k][0], t[0]), __dadd_rn(u[k][1], t[1]), __dadd_rn(u[k][2], t[2]), ok[k], max_sq, &sq);
+              id[k] = kdtree_nn1_warp(tv, __dadd_rn(u[k][0], tvec(0)), __dadd_rn(u[k][1], tvec(1)), __dadd_rn(u[k][2], tvec(2)), ok[k], max_sq, &sq);
             }
             if (ok[k]) corr[base + k * 32] = id[k];
           }
@@ -404,7 +422,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             prefetch_l2(rec + 72);
 #endif
           }
-          if (B2_WS_PREFETCH_OPERANDS && lane < 12) {
+          if (B2_WS_PREFETCH_OPERANDS && KIND <= 1 && lane < 12) {
             // covariance lines of this 32-point group: 6 planes x 2 halves of 16 points
             const uint32_t half = lane & 1, plane = lane >> 1;
             if ((mask[k] >> (16 * half)) & 0xffffu) prefetch_l2(cv + plane * n_pad + (base - lane) + k * 32 + 16 * half);
@@ -438,27 +456,34 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     uint32_t tile = tile_lo;
     double acc[kAcc];
     while (tile < tile_hi) {
-      const uint32_t f = __ldg(tile_factor + tile);
+      const uint32_t f = SINGLE ? 0u : __ldg(tile_factor + tile);
       consumer_barrier();  // previous flush is done with sh.desc
       if (ctid < static_cast<int>(sizeof(FactorDesc) / 4)) reinterpret_cast<uint32_t*>(&sh.desc)[ctid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + ctid);
       consumer_barrier();
       const FactorDesc& d = sh.desc;
       if (ctid < 21) {
-        const double* pe = (MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16;
+        const double* pe = SINGLE ? pose.m : ((MODE == MODE_ERROR ? poses_eval : poses_lin) + static_cast<size_t>(d.out_index) * 16);
         const double* pl = (MODE == MODE_ERROR) ? d.lin_pose : pe;
         if (ctid < 9)
-          sh.R[ctid] = __ldg(pe + (ctid / 3) * 4 + ctid % 3);
+          sh.R[ctid] = pe[(ctid / 3) * 4 + ctid % 3];
         else if (ctid < 12)
-          sh.t[ctid - 9] = __ldg(pe + (ctid - 9) * 4 + 3);
+          sh.t[ctid - 9] = pe[(ctid - 9) * 4 + 3];
         else
-          sh.RL[ctid - 12] = __ldg(pl + ((ctid - 12) / 3) * 4 + (ctid - 12) % 3);
+          sh.RL[ctid - 12] = pl[((ctid - 12) / 3) * 4 + (ctid - 12) % 3];
       }
       consumer_barrier();
-      double RL[9], t[3];
+      constexpr bool kConstRL = SINGLE && MODE == MODE_LINEARIZE;
+      double RLr[kConstRL ? 1 : 9], tr[SINGLE ? 1 : 3];
+      if (!kConstRL) {
 #pragma unroll
-      for (int k = 0; k < 9; k++) RL[k] = sh.RL[k];
+        for (int k = 0; k < 9; k++) RLr[k] = sh.RL[k];
+      }
+      if (!SINGLE) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) t[k] = sh.t[k];
+        for (int k = 0; k < 3; k++) tr[k] = sh.t[k];
+      }
+      auto rl = [&](int i) -> double { return kConstRL ? pose.m[(i / 3) * 4 + (i % 3)] : RLr[kConstRL ? 0 : i]; };
+      auto tt = [&](int i) -> double { return SINGLE ? pose.m[i * 4 + 3] : tr[SINGLE ? 0 : i]; };
 #pragma unroll
       for (int k = 0; k < kAcc; k++) acc[k] = 0.0;
       const double* __restrict__ records = d.records;
@@ -513,7 +538,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
             const uint32_t nj = nb > 32u * j ? min(32u, nb - 32u * j) : 0u;
             load_meta(b[j], rings + static_cast<size_t>(p) * 2 * kRing, hd + 32u * j, nj, lane);
 #ifndef B2_WS_DEBUG_NO_ACCUM
-            load_operands<CT>(b[j], records, cv, n_pad);  // lanes beyond nj gather element 0 (valid memory), masked below
+            load_operands<CT, KIND>(b[j], records, cv, n_pad);  // lanes beyond nj gather element 0 (valid memory), masked below
 #endif
           }
 #pragma unroll
@@ -527,11 +552,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
           if (nb == kBatch) {
             // full batch (uniform branch): no per-lane predicates, the kIPL bodies sit in one basic block and interleave
 #pragma unroll
-            for (int j = 0; j < kIPL; j++) accumulate_point<MODE>(acc, RL, t, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
+            for (int j = 0; j < kIPL; j++) accumulate_point_f<MODE, MetricOf<KIND>::value>(acc, rl, tt, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
           } else {
 #pragma unroll
             for (int j = 0; j < kIPL; j++)
-              if (b[j].valid) accumulate_point<MODE>(acc, RL, t, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
+              if (b[j].valid) accumulate_point_f<MODE, MetricOf<KIND>::value>(acc, rl, tt, b[j].u0, b[j].u1, b[j].u2, b[j].T, b[j].A);
           }
 #endif
         }
@@ -550,7 +575,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 2], globaltimer());
       if (lane == 0) atomicMin(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());
 #endif
-      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, poses_lin, sig);
+      flush_factor<MODE>(sh, acc, ctid, partials, counters, out, SINGLE ? pose.m : (poses_lin + static_cast<size_t>(sh.desc.out_index) * 16), sig);
       tile = run_end;
     }
   }

@@ -294,11 +294,24 @@ __device__ __forceinline__ double rcp_nr(double x) {
 
 // RLf(i) / tf(i): accessors of the linearization rotation (row-major) and the translation of the evaluation pose -- arrays in
 // registers, or by-value kernel parameters (constant-bank operands) for single-factor launches.
-template <int MODE, class RLF, class TF>
+// METRIC selects the weight matrix M of r^T M r:
+//   0  GICP / VGICP: M = (C_B + RL C_A RL^T)^-1                              (integrated_gicp_factor_impl.hpp:177-183)
+//   1  point-to-point ICP: M = I                                             (integrated_icp_factor_impl.hpp:205-248)
+//   2  point-to-plane ICP: M = diag(n_x^2, n_y^2, n_z^2), n = target normal  (residual and Jacobian rows scaled by n: N^T N)
+//      -- the normal travels in the record's first three covariance slots.
+template <int MODE, int METRIC = 0, class RLF, class TF>
 __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RLF& RLf, const TF& tf, double v0, double v1, double v2, const TargetRec& T,
                                                    const SourceCov& A) {
   const double mb0 = T.r01.x, mb1 = T.r01.y, mb2 = T.r23.x;
   const double b00 = T.r23.y, b01 = T.r45.x, b02 = T.r45.y, b11 = T.r67.x, b12 = T.r67.y, b22 = T.r89.x;
+  double m00, m01, m02, m11, m12, m22;
+  if (METRIC == 1) {
+    m00 = m11 = m22 = 1.0;
+    m01 = m02 = m12 = 0.0;
+  } else if (METRIC == 2) {
+    m00 = b00 * b00, m11 = b01 * b01, m22 = b02 * b02;
+    m01 = m02 = m12 = 0.0;
+  } else {
   // fused covariance S = C_B + RL C_A RL^T (symmetric), M = S^-1 (cofactors / det)
   const double t00 = RLf(0) * A.a00 + RLf(1) * A.a01 + RLf(2) * A.a02;
   const double t01 = RLf(0) * A.a01 + RLf(1) * A.a11 + RLf(2) * A.a12;
@@ -323,8 +336,9 @@ __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RL
   const double c12 = s01 * s02 - s00 * s12;
   const double c22 = s00 * s11 - s01 * s01;
   const double inv_det = rcp_nr(s00 * c00 + s01 * c01 + s02 * c02);
-  const double m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
-  const double m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
+  m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
+  m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
+  }
 
   // residual r = mean_B - (u + t), Mahalanobis error
   const double e0 = mb0 - __dadd_rn(v0, tf(0)), e1 = mb1 - __dadd_rn(v1, tf(1)), e2 = mb2 - __dadd_rn(v2, tf(2));
@@ -371,10 +385,10 @@ __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RL
   }
 }
 
-template <int MODE>
+template <int MODE, int METRIC = 0>
 __device__ __forceinline__ void accumulate_point(double (&acc)[kAcc], const double (&RL)[9], const double (&t)[3], double v0, double v1, double v2,
                                                  const TargetRec& T, const SourceCov& A) {
-  accumulate_point_f<MODE>(acc, [&](int i) { return RL[i]; }, [&](int i) { return t[i]; }, v0, v1, v2, T, A);
+  accumulate_point_f<MODE, METRIC>(acc, [&](int i) { return RL[i]; }, [&](int i) { return t[i]; }, v0, v1, v2, T, A);
 }
 
 // u = R p : coefficient sums in index order, each operation individually rounded (bit-parity with the CPU float64 path)
@@ -387,6 +401,50 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 }  // namespace b2
 
 // ---- kernel configurations -------------------------------------------------------------------------------------
+// Which kernel serves the VGICP path: 1 = the warp-specialised register-pipelined kernel (b2_factor_kernel_ws.cuh), 2 = the
+// TMA / cp.async staged kernel (b2_factor_kernel_v2.cuh).  The default is whichever measured faster on B200
+// (profiles/r02_experiments.md); both pass the same parity tests.
+#ifndef B2_VGICP_IMPL
+#define B2_VGICP_IMPL 1
+#endif
+#define B2_WS_NAMESPACE ws
+#ifndef B2_WS_PRODUCERS
+#define B2_WS_PRODUCERS 8
+#endif
+#ifndef B2_WS_CONSUMERS
+#define B2_WS_CONSUMERS 8
+#endif
+#ifndef B2_WS_REGS_PRODUCER
+#define B2_WS_REGS_PRODUCER 88
+#endif
+#ifndef B2_WS_REGS_CONSUMER
+#define B2_WS_REGS_CONSUMER 168
+#endif
+#ifndef B2_WS_RING
+#define B2_WS_RING 256
+#endif
+#ifndef B2_WS_PPL
+#define B2_WS_PPL 2
+#endif
+#ifndef B2_WS_IPL
+#define B2_WS_IPL 1
+#endif
+#ifndef B2_WS_COORDS_AHEAD
+#define B2_WS_COORDS_AHEAD 0
+#endif
+#ifndef B2_WS_PREFETCH_OPERANDS
+#define B2_WS_PREFETCH_OPERANDS 1
+#endif
+#include "b2_factor_kernel_ws.cuh"
+#undef B2_WS_NAMESPACE
+#undef B2_WS_PRODUCERS
+#undef B2_WS_CONSUMERS
+#undef B2_WS_REGS_PRODUCER
+#undef B2_WS_REGS_CONSUMER
+#undef B2_WS_RING
+#undef B2_WS_PPL
+#undef B2_WS_IPL
+
 // VGICP (voxel hash probe): the v2 kernel (TMA-staged streams, shared-memory-fed accumulate warps).
 #define B2_V2_NAMESPACE v2
 #ifndef B2_V2_PRODUCERS
@@ -396,10 +454,10 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_V2_CONSUMERS 8
 #endif
 #ifndef B2_V2_REGS_PRODUCER
-#define B2_V2_REGS_PRODUCER 104
+#define B2_V2_REGS_PRODUCER 72
 #endif
 #ifndef B2_V2_REGS_CONSUMER
-#define B2_V2_REGS_CONSUMER 120
+#define B2_V2_REGS_CONSUMER 128
 #endif
 #ifndef B2_V2_RING
 #define B2_V2_RING 128
@@ -408,7 +466,16 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_V2_PPL 2
 #endif
 #ifndef B2_V2_XYZ_STAGES
-#define B2_V2_XYZ_STAGES 4
+#define B2_V2_XYZ_STAGES 3
+#endif
+#ifndef B2_V2_BACKOFF_MIN
+#define B2_V2_BACKOFF_MIN 32u  // ns: first sleep of a waiting warp
+#endif
+#ifndef B2_V2_BACKOFF_MAX
+#define B2_V2_BACKOFF_MAX 128u
+#endif
+#ifndef B2_V2_BUCKET_STAGES
+#define B2_V2_BUCKET_STAGES 3  // probe warps request bucket groups 2 tiles ahead
 #endif
 #ifndef B2_V2_PREFETCH_GROUPS
 #define B2_V2_PREFETCH_GROUPS 0  // phase A starts every point's bucket group towards L2 (only useful with B2_V2_PIPELINE_A)
@@ -469,6 +536,21 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 using KernelFn = void (*)(const FactorDesc*, const uint32_t*, uint32_t, const double*, const double*, double*, unsigned int*, double*, DoneSignal, PoseArg, const uint32_t*);
 
+#if B2_VGICP_IMPL == 1
+namespace vgicp = ws;
+template <int MODE, bool SINGLE>
+KernelFn pick_vgicp(int pb, int cb) {
+  if (pb == 4 && cb == 4) return ws::factor_kernel<float, float, 0, MODE, SINGLE>;
+  if (pb == 4 && cb == 8) return ws::factor_kernel<float, double, 0, MODE, SINGLE>;
+  if (pb == 8 && cb == 4) return ws::factor_kernel<double, float, 0, MODE, SINGLE>;
+  return ws::factor_kernel<double, double, 0, MODE, SINGLE>;
+}
+template <int MODE>
+size_t vgicp_smem(int, int) {
+  return ws::kRingBytes;
+}
+#else
+namespace vgicp = v2;
 template <int MODE, bool SINGLE>
 KernelFn pick_vgicp(int pb, int cb) {
   if (pb == 4 && cb == 4) return v2::factor_kernel<float, float, 0, MODE, SINGLE>;
@@ -483,6 +565,7 @@ size_t vgicp_smem(int pb, int cb) {
   if (pb == 8 && cb == 4) return v2::Layout<double, float, MODE>::kTotal;
   return v2::Layout<double, double, MODE>::kTotal;
 }
+#endif
 template <int MODE>
 KernelFn pick_gicp(int pb, int cb) {
   if (pb == 4 && cb == 4) return ws_gicp::factor_kernel<float, float, 1, MODE>;
@@ -490,13 +573,19 @@ KernelFn pick_gicp(int pb, int cb) {
   if (pb == 8 && cb == 4) return ws_gicp::factor_kernel<double, float, 1, MODE>;
   return ws_gicp::factor_kernel<double, double, 1, MODE>;
 }
+// ICP / point-to-plane ICP: the same kd-tree kernel with M = I / diag(n^2); no source covariance is read (CT is a dummy)
+template <int MODE>
+KernelFn pick_icp(int kind, int pb) {
+  if (kind == B2_FACTOR_ICP) return pb == 4 ? ws_gicp::factor_kernel<float, float, 2, MODE> : ws_gicp::factor_kernel<double, float, 2, MODE>;
+  return pb == 4 ? ws_gicp::factor_kernel<float, float, 3, MODE> : ws_gicp::factor_kernel<double, float, 3, MODE>;
+}
 
 // launch shape of a kernel configuration
 struct KernelShape {
   int threads, tile;
 };
 KernelShape kernel_shape(int kind) {
-  if (kind == 0) return {v2::kThreads, v2::kTile};
+  if (kind == 0) return {vgicp::kThreads, vgicp::kTile};
   return {ws_gicp::kThreads, ws_gicp::kTile};
 }
 size_t kernel_smem(int kind, int mode, int pb, int cb) {
@@ -510,6 +599,7 @@ KernelFn pick_kernel(int kind, int mode, int pb, int cb, bool single) {
     if (single) return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, true>(pb, cb) : pick_vgicp<MODE_ERROR, true>(pb, cb);
     return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, false>(pb, cb) : pick_vgicp<MODE_ERROR, false>(pb, cb);
   }
+  if (kind >= B2_FACTOR_ICP) return mode == MODE_LINEARIZE ? pick_icp<MODE_LINEARIZE>(kind, pb) : pick_icp<MODE_ERROR>(kind, pb);
   return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE>(pb, cb) : pick_gicp<MODE_ERROR>(pb, cb);
 }
 
@@ -575,6 +665,24 @@ __global__ void build_target_records_kernel(const PT* __restrict__ pts, const CT
   r[2] = static_cast<double>(pts[2 * n_pad + s]);
 #pragma unroll
   for (int k = 0; k < 6; k++) r[3 + k] = static_cast<double>(covs[k * n_pad + s]);
+  r[9] = 1.0;
+}
+
+// ICP: target records (mean | normal or zeros | 1) in the tree's leaf order; normals are a host array in caller order (n x 3)
+template <typename PT>
+__global__ void build_icp_records_kernel(const PT* __restrict__ pts, size_t n_pad, const uint32_t* __restrict__ cloud_inv_perm, const uint32_t* __restrict__ leaf_index,
+                                         const double* __restrict__ normals, size_t n, double* __restrict__ records) {
+  const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t caller = leaf_index[j];
+  const size_t s = cloud_inv_perm ? cloud_inv_perm[caller] : caller;
+  double* r = records + j * kRecordDoubles;
+  r[0] = static_cast<double>(pts[s]);
+  r[1] = static_cast<double>(pts[n_pad + s]);
+  r[2] = static_cast<double>(pts[2 * n_pad + s]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) r[3 + k] = normals ? normals[static_cast<size_t>(caller) * 3 + k] : 0.0;
+  r[6] = r[7] = r[8] = 0.0;
   r[9] = 1.0;
 }
 
@@ -792,6 +900,63 @@ b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const
   return B2_OK;
 }
 
+b2_status b2_icp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const b2_kdtree* tree, const b2_cloud* source, int use_point_to_plane, const double* target_normals,
+                               b2_factor** out) {
+  B2_REQUIRE(out != nullptr, "b2_icp_factor_create: out is NULL");
+  *out = nullptr;
+  B2_REQUIRE(ctx != nullptr, "b2_icp_factor_create: ctx is NULL");
+  // reference aborts on these (integrated_icp_factor_impl.hpp:37-45)
+  B2_REQUIRE(target_cloud != nullptr && target_cloud->d_points != nullptr && (!use_point_to_plane || target_normals != nullptr), "error: target frame doesn't have required attributes for icp");
+  B2_REQUIRE(source != nullptr && source->d_points != nullptr, "error: source frame doesn't have required attributes for icp");
+  B2_REQUIRE(tree != nullptr && tree->n == target_cloud->n, "b2_icp_factor_create: the tree was not built over the target cloud");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  b2_factor* f = new b2_factor;
+  f->ctx = ctx;
+  f->kind = use_point_to_plane ? B2_FACTOR_ICP_PLANE : B2_FACTOR_ICP;
+  f->target = target_cloud;
+  f->tree = tree;
+  f->source = source;
+  const size_t nt = tree->n;
+  cudaError_t e;
+  uint32_t* d_inv = nullptr;
+  double* d_normals = nullptr;
+  auto bail = [&](b2_status stt) {
+    if (d_inv) cudaFree(d_inv);
+    if (d_normals) cudaFree(d_normals);
+    b2_factor_destroy(f);
+    return stt;
+  };
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&f->d_corr), std::max<size_t>(source->n_pad, 1) * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&f->d_lin_pose), 16 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&f->d_target_records), std::max<size_t>(nt, 1) * kRecordDoubles * sizeof(double))) != cudaSuccess) {
+    return bail(fail(B2_ERR_OUT_OF_MEMORY, "b2_icp_factor_create: %s", cudaGetErrorString(e)));
+  }
+  if (nt > 0) {
+    const unsigned grid = static_cast<unsigned>((nt + 255) / 256);
+    if (target_cloud->d_perm) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&d_inv), nt * sizeof(uint32_t))) != cudaSuccess) return bail(fail(B2_ERR_OUT_OF_MEMORY, "b2_icp_factor_create: %s", cudaGetErrorString(e)));
+      invert_perm_kernel<<<grid, 256, 0, st>>>(target_cloud->d_perm, nt, d_inv);
+    }
+    if (use_point_to_plane) {
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&d_normals), nt * 3 * sizeof(double))) != cudaSuccess ||
+          (e = cudaMemcpyAsync(d_normals, target_normals, nt * 3 * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return bail(fail(B2_ERR_OUT_OF_MEMORY, "b2_icp_factor_create: %s", cudaGetErrorString(e)));
+    }
+    if (target_cloud->point_bytes == 4)
+      build_icp_records_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(target_cloud->d_points), target_cloud->n_pad, d_inv, tree->d_leaf_index, d_normals, nt, f->d_target_records);
+    else
+      build_icp_records_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(target_cloud->d_points), target_cloud->n_pad, d_inv, tree->d_leaf_index, d_normals, nt, f->d_target_records);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(fail(B2_ERR_CUDA, "b2_icp_factor_create: %s", cudaGetErrorString(e)));
+  }
+  if (d_inv) cudaFree(d_inv);
+  if (d_normals) cudaFree(d_normals);
+  *out = f;
+  return B2_OK;
+}
+
 b2_status b2_factor_destroy(b2_factor* f) {
   if (!f) return B2_OK;
   cudaSetDevice(f->ctx->device);
@@ -835,7 +1000,7 @@ b2_status b2_factor_correspondences(const b2_factor* f, int64_t* out) {
   cudaStream_t st = f->ctx->stream;
   long long* d_out = nullptr;
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), n * sizeof(long long)));
-  scatter_corr_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f->d_corr, f->source->d_perm, f->kind == B2_FACTOR_GICP ? f->tree->d_leaf_index : nullptr, n, d_out);
+  scatter_corr_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f->d_corr, f->source->d_perm, f->kind != B2_FACTOR_VGICP ? f->tree->d_leaf_index : nullptr, n, d_out);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(long long), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -865,14 +1030,14 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
   std::map<std::tuple<int, int, int>, size_t> group_of;
   for (size_t i = 0; i < F; i++) {
     const b2_factor* f = factors[i];
-    const auto key = std::make_tuple(static_cast<int>(f->kind), f->source->point_bytes, f->source->cov_bytes);
+    const auto key = std::make_tuple(static_cast<int>(f->kind), f->source->point_bytes, f->kind >= B2_FACTOR_ICP ? 4 : f->source->cov_bytes);
     auto it = group_of.find(key);
     if (it == group_of.end()) {
       it = group_of.emplace(key, s->groups.size()).first;
       Group g;
       g.kind = f->kind;
       g.pb = f->source->point_bytes;
-      g.cb = f->source->cov_bytes;
+      g.cb = f->kind >= B2_FACTOR_ICP ? 4 : f->source->cov_bytes;
       s->groups.push_back(g);
     }
     s->groups[it->second].members.push_back(i);
@@ -925,7 +1090,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     auto keep_host_copy = [&]() { g.h_descs = descs; };
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb, false);
-      g.fn_single[mode] = (g.kind == B2_FACTOR_VGICP && F == 1) ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;
+      g.fn_single[mode] = (g.kind == B2_FACTOR_VGICP && F == 1) ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;  // by-value pose
       g.dyn_smem[mode] = kernel_smem(g.kind, mode, g.pb, g.cb);
       int per_sm = 0;
       cudaError_t e = cudaSuccess;
@@ -942,9 +1107,9 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
       // CTA c owns tiles [c T / G, (c + 1) T / G): a factor's partial-sum slots are the CTAs whose range touches it
       uint32_t c = 0;
       for (auto& d : descs) {
-        while (v2::cta_tile_begin(c + 1, g.num_tiles, G) <= d.tile_begin) c++;
+        while (vgicp::cta_tile_begin(c + 1, g.num_tiles, G) <= d.tile_begin) c++;
         uint32_t c_last = c;
-        while (v2::cta_tile_begin(c_last + 1, g.num_tiles, G) < d.tile_begin + d.num_tiles) c_last++;
+        while (vgicp::cta_tile_begin(c_last + 1, g.num_tiles, G) < d.tile_begin + d.num_tiles) c_last++;
         d.cta_first[mode] = c;
         d.num_slots[mode] = c_last - c + 1;
         d.slot_begin[mode] = slot_cursor;

@@ -132,7 +132,7 @@ struct b2_kdtree {
   size_t device_bytes = 0;
 };
 
-enum b2_factor_kind { B2_FACTOR_VGICP = 0, B2_FACTOR_GICP = 1 };
+enum b2_factor_kind { B2_FACTOR_VGICP = 0, B2_FACTOR_GICP = 1, B2_FACTOR_ICP = 2, B2_FACTOR_ICP_PLANE = 3 };
 
 struct b2_factor {
   b2_ctx* ctx = nullptr;

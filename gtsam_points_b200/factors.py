@@ -202,6 +202,47 @@ class IntegratedGICPFactor(IntegratedMatchingCostFactor):
         return IntegratedGICPFactor(a0, a1, self.target, self.source, target_tree=self.target_tree, ctx=self.ctx)
 
 
+class IntegratedICPFactor(IntegratedMatchingCostFactor):
+    """IntegratedICPFactor(target_key, source_key, target, source[, target_tree][, use_point_to_plane]) or
+    (fixed_target_pose, source_key, ...): include/gtsam_points/factors/integrated_icp_factor.hpp:27-145.  Point-to-plane
+    needs target normals (`target.normals`, n x 3).  Neither cloud needs covariances."""
+
+    def __init__(self, a0, a1, target: PointCloud, source: PointCloud, target_tree: KdTree | None = None, use_point_to_plane: bool = False, ctx: Context | None = None):
+        super().__init__(a0, a1)
+        normals = getattr(target, "normals", None)
+        if target is None or (use_point_to_plane and normals is None):
+            raise ValueError("error: target frame doesn't have required attributes for icp")
+        if source is None:
+            raise ValueError("error: source frame doesn't have required attributes for icp")
+        self.ctx = ctx or source.ctx
+        self.target, self.source, self.use_point_to_plane = target, source, bool(use_point_to_plane)
+        self.target_tree = target_tree or KdTree(target, ctx=self.ctx)
+        nrm = None
+        if use_point_to_plane:
+            nrm = np.ascontiguousarray(np.asarray(normals, dtype=np.float64)[:, :3])
+        h = C.c_void_p()
+        capi.check(capi.lib().b2_icp_factor_create(self.ctx.h, target.h, self.target_tree.h, source.h, 1 if use_point_to_plane else 0, capi.dptr(nrm) if nrm is not None else None, C.byref(h)))
+        self.h = h
+
+    def set_max_correspondence_distance(self, dist: float):
+        capi.check(capi.lib().b2_factor_set_max_correspondence_distance(self.h, float(dist)))
+
+    def set_correspondence_update_tolerance(self, angle: float, trans: float):
+        capi.check(capi.lib().b2_factor_set_correspondence_update_tolerance(self.h, float(angle), float(trans)))
+
+    def clone(self):
+        a0 = self._keys[0] if self.is_binary else self.fixed_target_pose
+        a1 = self._keys[1] if self.is_binary else self._keys[0]
+        return IntegratedICPFactor(a0, a1, self.target, self.source, target_tree=self.target_tree, use_point_to_plane=self.use_point_to_plane, ctx=self.ctx)
+
+
+class IntegratedPointToPlaneICPFactor(IntegratedICPFactor):
+    """integrated_icp_factor.hpp:147-175: IntegratedICPFactor with use_point_to_plane = true."""
+
+    def __init__(self, a0, a1, target: PointCloud, source: PointCloud, target_tree: KdTree | None = None, ctx: Context | None = None):
+        super().__init__(a0, a1, target, source, target_tree=target_tree, use_point_to_plane=True, ctx=ctx)
+
+
 class NonlinearFactorSetGPU:
     """Batches every device factor of a graph into one launch (NonlinearFactorSet interface)."""
 

@@ -61,8 +61,9 @@ class PointCloud:
     flags: capi.B2_CLOUD_* (default lossless storage, Morton-ordered on the device).
     """
 
-    def __init__(self, points, covs=None, ctx: Context | None = None, flags: int = capi.B2_CLOUD_DEFAULT):
+    def __init__(self, points, covs=None, ctx: Context | None = None, flags: int = capi.B2_CLOUD_DEFAULT, normals=None):
         self.ctx = ctx or default_context()
+        self.normals = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64)  # host side; used by point-to-plane ICP targets
         self.points = np.ascontiguousarray(points, dtype=np.float64)
         if self.points.ndim != 2 or self.points.shape[1] not in (3, 4):
             raise ValueError("points must be N x 3 or N x 4")

@@ -200,6 +200,12 @@ B2_API b2_status b2_kdtree_estimate_covariances(const b2_kdtree* tree, int k_nei
 B2_API b2_status b2_vgicp_factor_create(b2_ctx* ctx, const b2_voxelmap* target, const b2_cloud* source, b2_factor** out);
 /* target_cloud must carry covariances; tree must have been built over the same target points. */
 B2_API b2_status b2_gicp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const b2_kdtree* tree, const b2_cloud* source, b2_factor** out);
+/* IntegratedICPFactor_ / IntegratedPointToPlaneICPFactor_ (include/gtsam_points/factors/integrated_icp_factor.hpp:27-145,
+ * impl/integrated_icp_factor_impl.hpp:131-248): the same kd-tree search, residual r = mu_B - T p weighted with the identity
+ * (point-to-point) or, when use_point_to_plane != 0, scaled row-wise by the target point's normal (target_normals: host, n x 3,
+ * caller order).  Neither cloud needs covariances. */
+B2_API b2_status b2_icp_factor_create(b2_ctx* ctx, const b2_cloud* target_cloud, const b2_kdtree* tree, const b2_cloud* source, int use_point_to_plane,
+                                      const double* target_normals, b2_factor** out);
 B2_API b2_status b2_factor_destroy(b2_factor* f);
 /* IntegratedGICPFactor_::set_max_correspondence_distance (integrated_gicp_factor.hpp:98-101); default 1.0 */
 B2_API b2_status b2_factor_set_max_correspondence_distance(b2_factor* f, double dist);

@@ -353,3 +353,56 @@ def test_kdtree_ties_duplicate_points(g):
     c, oc = f.correspondences(), of.correspondences()
     assert np.array_equal(c >= 0, oc >= 0) and np.array_equal(tp[c[c >= 0]], tp[oc[oc >= 0]])
     assert_linearized_close(f._last, ref)
+
+
+@pytest.mark.parametrize("plane", [False, True])
+def test_icp_factors_match_oracle(g, scene, plane):
+    """IntegratedICPFactor / IntegratedPointToPlaneICPFactor (integrated_icp_factor_impl.hpp:131-248) on the kd-tree kernel
+    with M = I / diag(n^2): correspondences and H, b, error vs the oracle; error() with frozen correspondences; tolerance."""
+    tp, tc, sp, sc = scene
+    rng = np.random.default_rng(12)
+    normals = rng.normal(size=(len(tp), 3))
+    normals /= np.linalg.norm(normals, axis=1, keepdims=True)
+    tgt = g.PointCloud(tp, normals=normals)  # no covariances on either side
+    src = g.PointCloud(sp)
+    f = (g.IntegratedPointToPlaneICPFactor if plane else g.IntegratedICPFactor)(0, 1, tgt, src)
+    otgt = orc.Cloud(tp)
+    otgt.set_normals(normals)
+    of = orc.Factor(otgt, orc.Cloud(sp), tree=orc.KdTree(otgt, 4), num_threads=4, icp="plane" if plane else "point")
+    for max_dist in (1.0, 0.4):
+        f.set_max_correspondence_distance(max_dist)
+        of.set_max_correspondence_distance(max_dist)
+        values = {0: syn.random_pose(rng, 0.5, 3.0), 1: None}
+        values[1] = values[0] @ syn.random_pose(rng, 0.01, 0.1)
+        d = f.calc_delta(values)
+        f.linearize(values)
+        ref = of.linearize(d)
+        assert np.array_equal(f.correspondences(), of.correspondences())
+        assert ref["num_inliers"] > 5000
+        assert_linearized_close(f._last, ref)
+        v2 = {0: values[0], 1: values[0] @ syn.random_pose(rng, 0.01, 0.1)}
+        e, eref = f.error(v2), of.error(f.calc_delta(v2))
+        assert abs(e - eref) <= TOL * abs(eref)
+
+
+def test_gicp_correspondence_update_tolerance(g, scene):
+    """integrated_gicp_factor_impl.hpp:135-147 on the device: inside the tolerance the correspondences of the last association
+    are kept and linearized at the NEW pose (== oracle with the same setting); outside it the factor re-associates."""
+    tp, tc, sp, sc = scene
+    tgt, src = g.PointCloud(tp, tc), g.PointCloud(sp, sc)
+    f = g.IntegratedGICPFactor(0, 1, tgt, src)
+    f.set_correspondence_update_tolerance(0.05, 0.5)
+    otgt = orc.Cloud(tp, tc)
+    of = orc.Factor(otgt, orc.Cloud(sp, sc), tree=orc.KdTree(otgt, 4), num_threads=4)
+    of.set_correspondence_update_tolerance(0.05, 0.5)
+    rng = np.random.default_rng(8)
+    d0 = syn.random_pose(rng, 0.01, 0.1)
+    steps = [d0, d0 @ syn.se3_exp(np.array([0.01, -0.01, 0.005, 0.05, -0.05, 0.02])), d0 @ syn.se3_exp(np.array([0.2, 0, 0, 1.0, 0, 0])), d0]
+    corrs = []
+    for d in steps:
+        f.linearize({0: np.eye(4), 1: d})
+        ref = of.linearize(d)
+        assert np.array_equal(f.correspondences(), of.correspondences())
+        assert_linearized_close(f._last, ref)
+        corrs.append(f.correspondences().copy())
+    assert np.array_equal(corrs[0], corrs[1]) and not np.array_equal(corrs[1], corrs[2])  # frozen, then re-associated
