@@ -68,10 +68,11 @@ def pin_openmp_env():
     torch / the oracle are imported.  (Explicit user settings win.)"""
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")  # worker threads spin between the timed calls instead of being woken up for each
 
 
 def host_info():
-    info = {"nproc": os.cpu_count(), "affinity": len(AFFINITY), "omp_proc_bind": os.environ.get("OMP_PROC_BIND"), "omp_places": os.environ.get("OMP_PLACES")}
+    info = {"nproc": os.cpu_count(), "affinity": len(AFFINITY), "omp_proc_bind": os.environ.get("OMP_PROC_BIND"), "omp_places": os.environ.get("OMP_PLACES"), "omp_wait_policy": os.environ.get("OMP_WAIT_POLICY")}
     try:
         import psutil
 
@@ -575,7 +576,7 @@ def run_gpu(args):
                 "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": ncu_traffic(),
-                "kernel": "b2::v2::factor_kernel<float,double,VGICP,LINEARIZE,SINGLE>",
+                "kernel": "b2::ws::factor_kernel<float,double,VGICP,LINEARIZE,SINGLE> (by-value pose)",
                 "kernel_ms": kern_ms_mean,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_formula": "N*48 + N_buckets_ref*16 + V*52 + 992 with N_buckets_ref = 2^ceil(log2(2V)) (>= 16384)",

@@ -46,6 +46,11 @@ static_assert(kP % kC == 0, "every accumulate warp drains the same number of rin
 static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * 32 * kIPL + kWarpPoints, "ring capacity: a tile's hits + one batch of publication lag + one batch");
 static_assert(kWarpPoints * 4 % 128 == 0 || kPPL == 1, "coordinate prefetch works on whole lines");
 constexpr size_t kRingBytes = static_cast<size_t>(kP) * 2 * kRing * sizeof(double2);
+#ifndef B2_WS_KD_SMEM_STACK
+#define B2_WS_KD_SMEM_STACK 0
+#endif
+// dynamic shared memory of a launch: the rings, then (kd-tree kinds) one traversal-stack block per probe warp
+constexpr size_t kDynSmemBytes = kRingBytes + (B2_WS_KD_SMEM_STACK ? static_cast<size_t>(kP) * kKdSmemStackBytes : 0);
 
 constexpr unsigned kSpinLimit = 1u << 25;  // polls (with sleeps: >= 2 s, typically tens of seconds) before a wait traps: a protocol bug must not hang the GPU
 
@@ -394,7 +399,12 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
               }
             } else {
               double sq;
+#if B2_WS_KD_SMEM_STACK
+              id[k] = kdtree_nn1_warp_smem(tv, __dadd_rn(u[k][0], tvec(0)), __dadd_rn(u[k][1], tvec(1)), __dadd_rn(u[k][2], tvec(2)), ok[k], max_sq, &sq,
+                                           dyn_smem + kRingBytes + static_cast<size_t>(p) * kKdSmemStackBytes, lane);
+#else
               id[k] = kdtree_nn1_warp(tv, __dadd_rn(u[k][0], tvec(0)), __dadd_rn(u[k][1], tvec(1)), __dadd_rn(u[k][2], tvec(2)), ok[k], max_sq, &sq);
+#endif
             }
             if (ok[k]) corr[base + k * 32] = id[k];
           }

@@ -502,13 +502,18 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_WS_PREFETCH_OPERANDS 1
 #endif
 #ifndef B2_WS_GICP_PRODUCERS
-#define B2_WS_GICP_PRODUCERS 28
+#define B2_WS_GICP_PRODUCERS 24  // 24 probe warps: rings (96 KB) + shared-memory traversal stacks (123 KB) fit the SM
 #endif
+#undef B2_WS_KD_SMEM_STACK
+#ifndef B2_WS_GICP_SMEM_STACK
+#define B2_WS_GICP_SMEM_STACK 1
+#endif
+#define B2_WS_KD_SMEM_STACK B2_WS_GICP_SMEM_STACK
 #ifndef B2_WS_GICP_CONSUMERS
 #define B2_WS_GICP_CONSUMERS 4
 #endif
 #ifndef B2_WS_GICP_REGS_PRODUCER
-#define B2_WS_GICP_REGS_PRODUCER 48
+#define B2_WS_GICP_REGS_PRODUCER 56
 #endif
 #ifndef B2_WS_GICP_REGS_CONSUMER
 #define B2_WS_GICP_REGS_CONSUMER 168
@@ -547,7 +552,7 @@ KernelFn pick_vgicp(int pb, int cb) {
 }
 template <int MODE>
 size_t vgicp_smem(int, int) {
-  return ws::kRingBytes;
+  return ws::kDynSmemBytes;
 }
 #else
 namespace vgicp = v2;
@@ -566,12 +571,12 @@ size_t vgicp_smem(int pb, int cb) {
   return v2::Layout<double, double, MODE>::kTotal;
 }
 #endif
-template <int MODE>
+template <int MODE, bool SINGLE>
 KernelFn pick_gicp(int pb, int cb) {
-  if (pb == 4 && cb == 4) return ws_gicp::factor_kernel<float, float, 1, MODE>;
-  if (pb == 4 && cb == 8) return ws_gicp::factor_kernel<float, double, 1, MODE>;
-  if (pb == 8 && cb == 4) return ws_gicp::factor_kernel<double, float, 1, MODE>;
-  return ws_gicp::factor_kernel<double, double, 1, MODE>;
+  if (pb == 4 && cb == 4) return ws_gicp::factor_kernel<float, float, 1, MODE, SINGLE>;
+  if (pb == 4 && cb == 8) return ws_gicp::factor_kernel<float, double, 1, MODE, SINGLE>;
+  if (pb == 8 && cb == 4) return ws_gicp::factor_kernel<double, float, 1, MODE, SINGLE>;
+  return ws_gicp::factor_kernel<double, double, 1, MODE, SINGLE>;
 }
 // ICP / point-to-plane ICP: the same kd-tree kernel with M = I / diag(n^2); no source covariance is read (CT is a dummy)
 template <int MODE>
@@ -590,7 +595,7 @@ KernelShape kernel_shape(int kind) {
 }
 size_t kernel_smem(int kind, int mode, int pb, int cb) {
   if (kind == 0) return mode == MODE_LINEARIZE ? vgicp_smem<MODE_LINEARIZE>(pb, cb) : vgicp_smem<MODE_ERROR>(pb, cb);
-  return ws_gicp::kRingBytes;
+  return ws_gicp::kDynSmemBytes;
 }
 
 // single == true: the by-value-pose instantiation for launches that cover exactly one factor (VGICP kernel only)
@@ -599,8 +604,9 @@ KernelFn pick_kernel(int kind, int mode, int pb, int cb, bool single) {
     if (single) return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, true>(pb, cb) : pick_vgicp<MODE_ERROR, true>(pb, cb);
     return mode == MODE_LINEARIZE ? pick_vgicp<MODE_LINEARIZE, false>(pb, cb) : pick_vgicp<MODE_ERROR, false>(pb, cb);
   }
-  if (kind >= B2_FACTOR_ICP) return mode == MODE_LINEARIZE ? pick_icp<MODE_LINEARIZE>(kind, pb) : pick_icp<MODE_ERROR>(kind, pb);
-  return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE>(pb, cb) : pick_gicp<MODE_ERROR>(pb, cb);
+  if (kind >= B2_FACTOR_ICP) return single ? nullptr : (mode == MODE_LINEARIZE ? pick_icp<MODE_LINEARIZE>(kind, pb) : pick_icp<MODE_ERROR>(kind, pb));
+  if (single) return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE, true>(pb, cb) : pick_gicp<MODE_ERROR, true>(pb, cb);
+  return mode == MODE_LINEARIZE ? pick_gicp<MODE_LINEARIZE, false>(pb, cb) : pick_gicp<MODE_ERROR, false>(pb, cb);
 }
 
 // host-API sets up to this many factors use the zero-copy path (poses read from / results written to mapped pinned memory)
@@ -1090,7 +1096,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     auto keep_host_copy = [&]() { g.h_descs = descs; };
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb, false);
-      g.fn_single[mode] = (g.kind == B2_FACTOR_VGICP && F == 1) ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;  // by-value pose
+      g.fn_single[mode] = F == 1 ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;  // by-value pose (VGICP, GICP)
       g.dyn_smem[mode] = kernel_smem(g.kind, mode, g.pb, g.cb);
       int per_sm = 0;
       cudaError_t e = cudaSuccess;
