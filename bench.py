@@ -341,8 +341,11 @@ def run_gpu(args):
                 flush_w.fill_(i & 0xFF)
                 flush_r.sum()
 
-        def time_steps(step_fn, poses_c, warmup, steps):
-            """max-over-ranks device time of `steps` calls of step_fn(pose), L2 flushed before each, own CUDA events per step."""
+        def time_steps(step_fn, poses_c, warmup, steps, rendezvous=None):
+            """max-over-ranks device time of `steps` calls of step_fn(pose), L2 flushed before each, own CUDA events per step.
+            rendezvous (N > 1): enqueues a device-side rendezvous of the ranks' GPUs, so that the GPUs -- not the python
+            processes, whose launch skew is tens of microseconds -- enter each timed step together (the exchange inside a step
+            must not absorb another rank's L2 flush or host jitter; everything is enqueued ahead, nothing blocks the host)."""
             for i in range(warmup):
                 step_fn(poses_c[i])
             barrier()
@@ -350,7 +353,7 @@ def run_gpu(args):
             for i in range(steps):
                 flush_l2(i)
                 if world > 1:
-                    barrier()  # ranks enter the timed step together: the exchange must not absorb another rank's L2 flush
+                    (rendezvous or barrier)()
                 ev[i][0].record(stream)
                 step_fn(poses_c[warmup + i])
                 ev[i][1].record(stream)
@@ -385,7 +388,7 @@ def run_gpu(args):
         else:
             def dev_step(pose):
                 sset.linearize_device(pose)  # one launch: linearize + peer stores of the records + in-kernel flag wait
-        dev_total_ms, step_ms = time_steps(dev_step, poses_c, W, K)
+        dev_total_ms, step_ms = time_steps(dev_step, poses_c, W, K, sset.device_barrier)
         rec = sset.d_all.cpu().numpy().copy()
         exchange_path = "peer stores in the kernel epilogue (NVLink) + in-kernel flag wait (b2_exchange, CUDA IPC)" if sset.exchange is not None else "ONE all-reduce of [N x 128] f64 (NCCL)"
         if world > 1 and sset.exchange is not None:
@@ -406,7 +409,7 @@ def run_gpu(args):
         else:  # kernel-only timing for the roofline (same launch, no exchange)
             def kern_step(pose):
                 capi.check(issue_linearize(sset.set.h, pose.ctypes.data_as(dp), sset.d_local.data_ptr()))
-            _, kern_ms = time_steps(kern_step, poses_c, 1, K)
+            _, kern_ms = time_steps(kern_step, poses_c, 1, K, sset.device_barrier)
         kern_ms_mean = max_over_ranks(float(kern_ms.mean()))
 
         # ---- untimed parity check of the headline workload against the CPU oracle (rank 0; indices bit-exact, H / b 1e-9) ----
@@ -473,7 +476,7 @@ def run_gpu(args):
             def strong_step(pose):
                 total["rec"] = ss.linearize_device(pose).sum(0)  # the factor's H, b, error = sum of the ranks' partial records
 
-            ms_total, _ = time_steps(strong_step, poses0, W, K)
+            ms_total, _ = time_steps(strong_step, poses0, W, K, ss.device_barrier)
             strong = {"workload": "ONE 1M-pt VGICP factor, source points split over the ranks, partial H/b records summed", "scaling": "strong",
                       "ms_per_step": ms_total / K, "value": N_SOURCE * K / (ms_total * 1e-3), "unit": UNIT, "inliers": int(total["rec"][121].item())}
             del ss, part, vm0
@@ -506,7 +509,7 @@ def run_gpu(args):
             else:
                 def cfg4_step(pose):
                     s4.linearize_device(pose)
-            ms_total, _ = time_steps(cfg4_step, poses4, W, K)
+            ms_total, _ = time_steps(cfg4_step, poses4, W, K, s4.device_barrier)
             rec4 = s4.d_all.cpu().numpy()
             cfg4 = {"workload": f"ISAM2-style relinearize: {F4} VGICP factors x {N4} points per GPU in ONE launch ({world * F4} factors sharded over {world} GPU(s)), records exchanged",
                     "scaling": "weak", "factors_per_gpu": F4, "points_per_factor": N4, "ms_per_step": ms_total / K, "value": world * F4 * N4 * K / (ms_total * 1e-3), "unit": UNIT,

@@ -17,7 +17,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libb2points.so")
 
 SOURCES = ["b2_context.cu", "b2_cloud.cu", "b2_voxelmap.cu", "b2_kdtree.cu", "b2_factors.cu"]
-HEADERS = ["b2_internal.hpp", "b2_device.cuh", "b2_kdtree.cuh", "b2_factor_kernel_ws.cuh", "b2_factor_kernel_v2.cuh", os.path.join("..", "..", "include", "b2points.h")]
+HEADERS = ["b2_internal.hpp", "b2_device.cuh", "b2_kdtree.cuh", "b2_factor_kernel_ws.cuh", "b2_factor_kernel_v2.cuh", "b2_factor_kernel_split.cuh", "b2_factor_kernel_sr.cuh", os.path.join("..", "..", "include", "b2points.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"

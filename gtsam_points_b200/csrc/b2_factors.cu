@@ -299,9 +299,12 @@ __device__ __forceinline__ double rcp_nr(double x) {
 //   1  point-to-point ICP: M = I                                             (integrated_icp_factor_impl.hpp:205-248)
 //   2  point-to-plane ICP: M = diag(n_x^2, n_y^2, n_z^2), n = target normal  (residual and Jacobian rows scaled by n: N^T N)
 //      -- the normal travels in the record's first three covariance slots.
-template <int MODE, int METRIC = 0, class RLF, class TF>
+// MASKED: branch-free form for kernels that carry several points per lane through one basic block: `vf` is 1.0 for a real
+// correspondence and 0.0 for a lane without one (whose operands are any finite stand-ins); M is scaled by vf, so every
+// contribution of a masked lane is an exact zero, and the inlier count is kept by the caller (integer).
+template <int MODE, int METRIC = 0, bool MASKED = false, class RLF, class TF>
 __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RLF& RLf, const TF& tf, double v0, double v1, double v2, const TargetRec& T,
-                                                   const SourceCov& A) {
+                                                   const SourceCov& A, double vf = 1.0) {
   const double mb0 = T.r01.x, mb1 = T.r01.y, mb2 = T.r23.x;
   const double b00 = T.r23.y, b01 = T.r45.x, b02 = T.r45.y, b11 = T.r67.x, b12 = T.r67.y, b22 = T.r89.x;
   double m00, m01, m02, m11, m12, m22;
@@ -335,7 +338,8 @@ __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RL
   const double c11 = s00 * s22 - s02 * s02;
   const double c12 = s01 * s02 - s00 * s12;
   const double c22 = s00 * s11 - s01 * s01;
-  const double inv_det = rcp_nr(s00 * c00 + s01 * c01 + s02 * c02);
+  double inv_det = rcp_nr(s00 * c00 + s01 * c01 + s02 * c02);
+  if (MASKED) inv_det *= vf;
   m00 = c00 * inv_det, m01 = c01 * inv_det, m02 = c02 * inv_det;
   m11 = c11 * inv_det, m12 = c12 * inv_det, m22 = c22 * inv_det;
   }
@@ -346,7 +350,7 @@ __device__ __forceinline__ void accumulate_point_f(double (&acc)[kAcc], const RL
   const double w1 = m01 * e0 + m11 * e1 + m12 * e2;
   const double w2 = m02 * e0 + m12 * e1 + m22 * e2;
   acc[27] += e0 * w0 + e1 * w1 + e2 * w2;
-  acc[28] += 1.0;
+  if (!MASKED) acc[28] += 1.0;
 
   if (MODE == MODE_LINEARIZE) {
     // K = hat(u) M  (column j = u x M[:,j])
@@ -492,6 +496,11 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #include "b2_factor_kernel_v2.cuh"
 #undef B2_V2_NAMESPACE
 
+// VGICP as two launches: streaming correspondence search + persistent accumulate-only kernel (B2_VGICP_IMPL == 3)
+#include "b2_factor_kernel_split.cuh"
+// VGICP, single-role form: every warp runs the whole chain as a cp.async software pipeline (B2_VGICP_IMPL == 4)
+#include "b2_factor_kernel_sr.cuh"
+
 // GICP (kd-tree 1-NN): the tree walk is ~100 dependent loads per point, the accumulate work is unchanged -> many thin
 // probe warps (the walk keeps its stack in local memory and needs few registers) feeding 4 fat accumulate warps.
 #define B2_WS_NAMESPACE ws_gicp
@@ -554,6 +563,38 @@ template <int MODE>
 size_t vgicp_smem(int, int) {
   return ws::kDynSmemBytes;
 }
+#elif B2_VGICP_IMPL == 4
+namespace vgicp = sr;
+template <int MODE, bool SINGLE>
+KernelFn pick_vgicp(int pb, int cb) {
+  if (pb == 4 && cb == 4) return sr::factor_kernel<float, float, 0, MODE, SINGLE>;
+  if (pb == 4 && cb == 8) return sr::factor_kernel<float, double, 0, MODE, SINGLE>;
+  if (pb == 8 && cb == 4) return sr::factor_kernel<double, float, 0, MODE, SINGLE>;
+  return ws::factor_kernel<double, double, 0, MODE, SINGLE>;
+}
+template <int MODE>
+size_t vgicp_smem(int pb, int cb) {
+  if (pb == 4 && cb == 4) return sr::Layout<float, float, MODE>::kTotal;
+  if (pb == 4 && cb == 8) return sr::Layout<float, double, MODE>::kTotal;
+  if (pb == 8 && cb == 4) return sr::Layout<double, float, MODE>::kTotal;
+  return ws::kDynSmemBytes;
+}
+#elif B2_VGICP_IMPL == 3
+namespace vgicp = sp;
+template <int MODE, bool SINGLE>
+KernelFn pick_vgicp(int pb, int cb) {
+  if (pb == 4 && cb == 4) return sp::factor_kernel<float, float, 0, MODE, SINGLE>;
+  if (pb == 4 && cb == 8) return sp::factor_kernel<float, double, 0, MODE, SINGLE>;
+  if (pb == 8 && cb == 4) return sp::factor_kernel<double, float, 0, MODE, SINGLE>;
+  return sp::factor_kernel<double, double, 0, MODE, SINGLE>;
+}
+template <int MODE>
+size_t vgicp_smem(int pb, int cb) {
+  if (pb == 4 && cb == 4) return sp::StageLayout<float, float>::kTotal;
+  if (pb == 4 && cb == 8) return sp::StageLayout<float, double>::kTotal;
+  if (pb == 8 && cb == 4) return sp::StageLayout<double, float>::kTotal;
+  return sp::StageLayout<double, double>::kTotal;
+}
 #else
 namespace vgicp = v2;
 template <int MODE, bool SINGLE>
@@ -585,12 +626,32 @@ KernelFn pick_icp(int kind, int pb) {
   return pb == 4 ? ws_gicp::factor_kernel<float, float, 3, MODE> : ws_gicp::factor_kernel<double, float, 3, MODE>;
 }
 
+// correspondence-search kernel of the two-launch form (nullptr: the factor kernel searches itself)
+using ProbeFn = void (*)(const FactorDesc*, const uint32_t*, const double*, PoseArg, const uint32_t*);
+ProbeFn pick_probe(int kind, int pb, bool single) {
+#if B2_VGICP_IMPL == 3
+  if (kind == 0) {
+    if (single) return pb == 4 ? sp::probe_kernel<float, true> : sp::probe_kernel<double, true>;
+    return pb == 4 ? sp::probe_kernel<float, false> : sp::probe_kernel<double, false>;
+  }
+#endif
+  (void)kind, (void)pb, (void)single;
+  return nullptr;
+}
+
 // launch shape of a kernel configuration
 struct KernelShape {
   int threads, tile;
 };
-KernelShape kernel_shape(int kind) {
-  if (kind == 0) return {vgicp::kThreads, vgicp::kTile};
+#if B2_VGICP_IMPL == 4
+// float64 point AND covariance storage does not fit the single-role kernel's shared-memory slots: that (rare) storage mode
+// keeps the warp-specialised kernel
+inline bool vgicp_uses_ws(int pb, int cb) { return pb == 8 && cb == 8; }
+#else
+inline bool vgicp_uses_ws(int, int) { return false; }
+#endif
+KernelShape kernel_shape(int kind, int pb, int cb) {
+  if (kind == 0) return vgicp_uses_ws(pb, cb) ? KernelShape{ws::kThreads, ws::kTile} : KernelShape{vgicp::kThreads, vgicp::kTile};
   return {ws_gicp::kThreads, ws_gicp::kTile};
 }
 size_t kernel_smem(int kind, int mode, int pb, int cb) {
@@ -624,6 +685,7 @@ struct Group {
   uint32_t grid[2] = {0, 0};
   KernelFn fn[2] = {nullptr, nullptr};
   KernelFn fn_single[2] = {nullptr, nullptr};  // by-value-pose instantiation (only for sets of exactly one factor)
+  ProbeFn probe = nullptr, probe_single = nullptr;  // two-launch form: correspondence search before a linearize
   size_t dyn_smem[2] = {0, 0};
 };
 
@@ -811,7 +873,11 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
         g.vm_gen[k] = vgen;
       }
     }
-    (single ? g.fn_single[mode] : g.fn[mode])<<<g.grid[mode], kernel_shape(g.kind).threads, g.dyn_smem[mode], st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials,
+    if (mode == MODE_LINEARIZE && g.probe != nullptr) {
+      (single ? g.probe_single : g.probe)<<<g.num_tiles, kernel_shape(g.kind, g.pb, g.cb).tile, 0, st>>>(g.d_descs, g.d_tile_factor, d_lin, pa, d_frozen);
+      s->launches++;
+    }
+    (single ? g.fn_single[mode] : g.fn[mode])<<<g.grid[mode], kernel_shape(g.kind, g.pb, g.cb).threads, g.dyn_smem[mode], st>>>(g.d_descs, g.d_tile_factor, g.num_tiles, d_lin, d_eval, s->d_partials,
                                                                                                                   s->d_counters, d_out, sig, pa, d_frozen);
     s->launches++;
   }
@@ -1056,7 +1122,7 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
 
   uint32_t slot_cursor = 0;
   for (auto& g : s->groups) {
-    const KernelShape shape = kernel_shape(g.kind);
+    const KernelShape shape = kernel_shape(g.kind, g.pb, g.cb);
     std::vector<FactorDesc> descs(g.members.size());
     std::vector<uint32_t> tile_factor;
     uint32_t tile_cursor = 0;
@@ -1094,6 +1160,8 @@ b2_status b2_factor_set_create(b2_ctx* ctx, b2_factor* const* factors, size_t F,
     }
     g.num_tiles = tile_cursor;
     auto keep_host_copy = [&]() { g.h_descs = descs; };
+    g.probe = pick_probe(g.kind, g.pb, false);
+    g.probe_single = F == 1 ? pick_probe(g.kind, g.pb, true) : nullptr;
     for (int mode = 0; mode < 2; mode++) {
       g.fn[mode] = pick_kernel(g.kind, mode, g.pb, g.cb, false);
       g.fn_single[mode] = F == 1 ? pick_kernel(g.kind, mode, g.pb, g.cb, true) : nullptr;  // by-value pose (VGICP, GICP)
@@ -1340,7 +1408,8 @@ struct b2_exchange {
   b2_ctx* ctx = nullptr;
   int n = 1, rank = 0;
   size_t num_records = 0;
-  double* d_block = nullptr;          // [2][num_records][128] doubles, then 2 x 8 flag words (padded to 256 bytes)
+  double* d_block = nullptr;          // [2][num_records][128] doubles, then 2 x 8 flag words + 8 rendezvous words (padded to 256 bytes)
+  unsigned int barrier_seq = 0;       // rendezvous counter (monotonic: the words are never reset)
   double* peer_block[kMaxPeers] = {nullptr};
   bool ipc_opened[kMaxPeers] = {false};
   size_t rec_doubles() const { return num_records * B2_LINEARIZED_DOUBLES; }
@@ -1413,6 +1482,40 @@ b2_status b2_exchange_enable_peer(b2_exchange* ex, int peer_rank, const b2_excha
   if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(B2_ERR_CUDA, "b2_exchange_enable_peer: %s", cudaGetErrorString(e));
   (void)cudaGetLastError();
   ex->peer_block[peer_rank] = peer->d_block;
+  return B2_OK;
+}
+
+namespace {
+// Stream-ordered rendezvous of the GPUs of an exchange: raise word [my_rank] = seq in every GPU's rendezvous array, then wait
+// until every rank's word in THIS GPU's array has reached seq (monotonic counters, so a fast peer's next round cannot be missed).
+__global__ void rendezvous_kernel(DoneSignal sig) {
+  const int r = threadIdx.x;
+  if (r < sig.n_peers) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[r] + sig.my_rank) = sig.seq;
+    const volatile unsigned int* mine = sig.peer_flag[sig.my_rank];
+    unsigned polls = 0;
+    while (static_cast<int>(mine[r] - sig.seq) < 0) {
+      __nanosleep(64);
+      if (++polls > (1u << 28)) __trap();
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+}  // namespace
+
+b2_status b2_exchange_barrier(b2_exchange* ex) {
+  B2_REQUIRE(ex != nullptr, "b2_exchange_barrier: exchange is NULL");
+  for (int p = 0; p < ex->n; p++) B2_REQUIRE(ex->peer_block[p] != nullptr, "b2_exchange_barrier: rank %d has not been imported", p);
+  B2_CUDA(cudaSetDevice(ex->ctx->device));
+  DoneSignal sig{};
+  sig.n_peers = ex->n;
+  sig.my_rank = ex->rank;
+  sig.seq = ++ex->barrier_seq;
+  for (int p = 0; p < ex->n; p++) sig.peer_flag[p] = reinterpret_cast<unsigned int*>(ex->peer_block[p] + 2 * ex->rec_doubles()) + 16;
+  rendezvous_kernel<<<1, 32, 0, ex->ctx->stream>>>(sig);
+  B2_CUDA(cudaGetLastError());
   return B2_OK;
 }
 

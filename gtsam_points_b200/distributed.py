@@ -163,6 +163,16 @@ class ShardedFactorSet:
         self.d_all = _device_view(self.torch, ptr, (self.num_global, RECORD), self.device)
         return self.d_all
 
+    def device_barrier(self):
+        """Stream-ordered rendezvous of the ranks' GPUs (b2_exchange_barrier): what is enqueued next starts on every GPU within
+        microseconds, without the host processes synchronising.  Falls back to a torch.distributed barrier without the exchange."""
+        if self.exchange is not None:
+            self._enter_lib()
+            capi.check(capi.lib().b2_exchange_barrier(self.exchange["h"]))
+            self._leave_lib()
+        elif self.dist.is_available() and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+            self.dist.barrier(group=self.group)
+
     # -- device-resident step: poses already in self.d_deltas -----------------------------------------------------
     def linearize_device(self, h_deltas=None):
         """Local kernel launch(es) + the exchange; leaves all records in self.d_all (device).  Asynchronous.

@@ -299,6 +299,11 @@ B2_API b2_status b2_exchange_enable_peer(b2_exchange* ex, int peer_rank, const b
 B2_API b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* set, const double* deltas, size_t first_slot, unsigned int step);
 /* device pointer to the [num_records x 128] block of `step` (valid until step + 2 is issued) */
 B2_API const double* b2_exchange_records(const b2_exchange* ex, unsigned int step);
+/* Stream-ordered rendezvous of the exchange's GPUs (one tiny kernel on the context's stream: raise a word on every GPU, wait for
+ * every rank's word): work enqueued after it starts on all GPUs within a few microseconds of each other, whatever the skew
+ * between the host processes -- every rank must call it the same number of times.  No host synchronisation.
+ * (The reference has no multi-GPU path; NCCL's barrier costs a collective launch and a host-side wait.) */
+B2_API b2_status b2_exchange_barrier(b2_exchange* ex);
 /* Number of kernel launches issued by this set since creation (for bench.py's gpu_launches). */
 B2_API uint64_t b2_factor_set_launch_count(const b2_factor_set* set);
 
