@@ -511,18 +511,18 @@ __device__ __forceinline__ void rotate_point(const double (&R)[9], double x, dou
 #define B2_WS_PREFETCH_OPERANDS 1
 #endif
 #ifndef B2_WS_GICP_PRODUCERS
-#define B2_WS_GICP_PRODUCERS 24  // 24 probe warps: rings (96 KB) + shared-memory traversal stacks (123 KB) fit the SM
+#define B2_WS_GICP_PRODUCERS 28  // (with B2_WS_GICP_SMEM_STACK at most 24: rings 96 KB + traversal stacks 99 KB)
 #endif
 #undef B2_WS_KD_SMEM_STACK
 #ifndef B2_WS_GICP_SMEM_STACK
-#define B2_WS_GICP_SMEM_STACK 1
+#define B2_WS_GICP_SMEM_STACK 0  // traversal stack in shared memory instead of local memory: measured slower (479 vs 412 us on cfg3, 24 x 56 vs 28 x 48 registers)
 #endif
 #define B2_WS_KD_SMEM_STACK B2_WS_GICP_SMEM_STACK
 #ifndef B2_WS_GICP_CONSUMERS
 #define B2_WS_GICP_CONSUMERS 4
 #endif
 #ifndef B2_WS_GICP_REGS_PRODUCER
-#define B2_WS_GICP_REGS_PRODUCER 56
+#define B2_WS_GICP_REGS_PRODUCER 48
 #endif
 #ifndef B2_WS_GICP_REGS_CONSUMER
 #define B2_WS_GICP_REGS_CONSUMER 168
