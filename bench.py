@@ -357,6 +357,9 @@ def run_gpu(args):
                 ev[i][0].record(stream)
                 step_fn(poses_c[warmup + i])
                 ev[i][1].record(stream)
+            # drain the device BEFORE the next collective: an NCCL kernel enqueued while persistent one-CTA-per-SM kernels that wait
+            # for a peer are still queued can take the SMs those kernels need on one rank and wait for them on the other (deadlock)
+            torch.cuda.synchronize(dev)
             barrier()
             ms = np.array([a.elapsed_time(b) for a, b in ev])
             return max_over_ranks(float(ms.sum())), ms
@@ -476,9 +479,9 @@ def run_gpu(args):
             def strong_step(pose):
                 total["rec"] = ss.linearize_device(pose).sum(0)  # the factor's H, b, error = sum of the ranks' partial records
 
-            ms_total, _ = time_steps(strong_step, poses0, W, K, ss.device_barrier)
+            ms_total, strong_ms = time_steps(strong_step, poses0, W, K, ss.device_barrier)
             strong = {"workload": "ONE 1M-pt VGICP factor, source points split over the ranks, partial H/b records summed", "scaling": "strong",
-                      "ms_per_step": ms_total / K, "value": N_SOURCE * K / (ms_total * 1e-3), "unit": UNIT, "inliers": int(total["rec"][121].item())}
+                      "ms_per_step": ms_total / K, "step_ms_min_median_max": [float(strong_ms.min()), float(np.median(strong_ms)), float(strong_ms.max())], "value": N_SOURCE * K / (ms_total * 1e-3), "unit": UNIT, "inliers": int(total["rec"][121].item())}
             del ss, part, vm0
 
         # ================= sub-record: cfg4 share -- 32 factors x 200k points per GPU in ONE set (256 factors at 8 GPUs) =================

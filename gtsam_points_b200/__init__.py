@@ -18,6 +18,6 @@ from .factors import (  # noqa: F401
     NonlinearFactorSetGPU,
     pose_inverse,
 )
-from .types import Context, GaussianVoxelMapGPU, KdTree, PointCloud, default_context, estimate_covariances, overlap_gpu  # noqa: F401
+from .types import Context, GaussianVoxelMapGPU, KdTree, PointCloud, default_context, estimate_covariances, merge_frames_gpu, overlap_gpu  # noqa: F401
 
 __version__ = "0.1.0"

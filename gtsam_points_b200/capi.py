@@ -66,6 +66,7 @@ SIGNATURES = {
     "b2_voxelmap_save_compact": (C.c_int, [_vp, C.c_char_p]),
     "b2_voxelmap_load": (C.c_int, [_vp, C.c_char_p, _pp]),
     "b2_overlap": (C.c_int, [_pp, C.c_size_t, _vp, _dp, _dp]),
+    "b2_merge_frames": (C.c_int, [_vp, _dp, C.POINTER(C.c_void_p), C.c_size_t, C.c_double, _dp, _dp, C.POINTER(C.c_size_t)]),
     "b2_voxelmap_lookup": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, _ip]),
     "b2_kdtree_create": (C.c_int, [_vp, _dp, C.c_int, C.c_size_t, _pp]),
     "b2_kdtree_destroy": (C.c_int, [_vp]),

@@ -49,6 +49,9 @@ constexpr size_t kRingBytes = static_cast<size_t>(kP) * 2 * kRing * sizeof(doubl
 #ifndef B2_WS_KD_SMEM_STACK
 #define B2_WS_KD_SMEM_STACK 0
 #endif
+#ifndef B2_WS_HEAD_FENCE
+#define B2_WS_HEAD_FENCE 1
+#endif
 // dynamic shared memory of a launch: the rings, then (kd-tree kinds) one traversal-stack block per probe warp
 constexpr size_t kDynSmemBytes = kRingBytes + (B2_WS_KD_SMEM_STACK ? static_cast<size_t>(kP) * kKdSmemStackBytes : 0);
 
@@ -273,7 +276,9 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       const uint32_t out_index = dg->out_index;
       // correspondence-update tolerance (integrated_gicp_factor_impl.hpp:135-147): the host decided that this factor's pose moved
       // less than its tolerances since the last association -> keep the stored correspondences, linearize them at the new pose
-      const bool frozen = MODE == MODE_ERROR || (frozen_flags != nullptr && __ldg(frozen_flags + out_index) != 0u);
+      // (the voxel path always re-associates -- integrated_vgicp_factor_impl.hpp:99 has no tolerance test -- so for KIND 0 this is a
+      // compile-time constant and costs the probe warps neither registers nor branches)
+      const bool frozen = MODE == MODE_ERROR || (KIND != 0 && frozen_flags != nullptr && __ldg(frozen_flags + out_index) != 0u);
       const PT* __restrict__ px = static_cast<const PT*>(dg->pts);
       const CT* __restrict__ cv = static_cast<const CT*>(dg->covs);
       const double* __restrict__ records = dg->records;
@@ -520,7 +525,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
         // Hand back the slots of every batch taken so far.  All lanes must have finished reading them: converge the warp,
         // then release (independent thread scheduling gives no such guarantee by itself).
         __syncwarp();
+#if B2_WS_HEAD_FENCE
         if (lane == 0) st_release(&sh.head[p], hd);
+#else
+        if (lane == 0) st_volatile(&sh.head[p], hd);
+#endif
         uint32_t nb = 0u;
         bool fin = false;
         {

@@ -12,6 +12,7 @@
 // order), a scan over segment heads, one more sort of the segments by first-touch index, then one thread per voxel
 // accumulates its points sequentially.  Everything is deterministic.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <cstdio>
@@ -228,6 +229,116 @@ __global__ void overlap_kernel(const PT* __restrict__ pts, size_t n, size_t n_pa
   const unsigned b = __ballot_sync(0xffffffffu, hit);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, static_cast<unsigned long long>(__popc(b)));
 }
+
+// ---- merge_frames (src/gtsam_points/types/gaussian_voxelmap_cpu_funcs.cpp:25-113; GPU twin gaussian_voxelmap_gpu_funcs.cu:196-330) ----
+// Several posed frames -> one downsampled cloud: 3 x 21-bit voxel keys of the points in the FIRST frame's coordinates, one
+// stable radix sort of (key, frame-major caller index), one thread per voxel sums the WORLD points and covariances of its
+// segment in (frame, point) order -- the CPU function's summation order, so the result is bit-identical to it.
+struct MergeFrame {
+  const void* pts;
+  const void* covs;
+  const uint32_t* perm;      // stored position -> caller index (nullptr: identity)
+  const uint32_t* inv_perm;  // caller index -> stored position (nullptr: identity)
+  uint32_t n, n_pad;
+  uint32_t offset;           // first global (frame-major) index of this frame
+  int point_bytes, cov_bytes;
+  double rel[12];            // rows of first_pose^-1 * pose (voxel keys)
+  double pose[12];           // rows of pose (sums)
+};
+constexpr unsigned long long kMergeNoKey = ~0ull;
+
+__device__ __forceinline__ double merge_ld(const void* base, int bytes, size_t i) {
+  return bytes == 4 ? static_cast<double>(static_cast<const float*>(base)[i]) : static_cast<const double*>(base)[i];
+}
+__device__ __forceinline__ int merge_frame_of(const MergeFrame* __restrict__ frames, int F, uint32_t g) {
+  int lo = 0, hi = F - 1;
+  while (lo < hi) {  // last frame whose offset <= g (empty frames share an offset with their successor: skip them)
+    const int mid = (lo + hi + 1) >> 1;
+    if (frames[mid].offset <= g) lo = mid; else hi = mid - 1;
+  }
+  while (frames[lo].n == 0u && lo + 1 < F) lo++;
+  return lo;
+}
+
+__global__ void merge_keys_kernel(const MergeFrame* __restrict__ frames, int f, double inv_res, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const MergeFrame& fr = frames[f];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // stored position
+  if (i >= fr.n) return;
+  const double x = merge_ld(fr.pts, fr.point_bytes, i), y = merge_ld(fr.pts, fr.point_bytes, fr.n_pad + i), z = merge_ld(fr.pts, fr.point_bytes, 2ull * fr.n_pad + i);
+  unsigned long long key = 0ull;
+  bool out_of_range = false;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const double q = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(fr.rel[r * 4 + 0], x), __dmul_rn(fr.rel[r * 4 + 1], y)), __dmul_rn(fr.rel[r * 4 + 2], z)), fr.rel[r * 4 + 3]);
+    const long long c = static_cast<long long>(voxel_coord1(q, inv_res)) + (1ll << 20);
+    if (c < 0 || c > ((1ll << 21) - 1)) out_of_range = true;
+    key |= (static_cast<unsigned long long>(c) & ((1ull << 21) - 1)) << (21 * r);
+  }
+  const uint32_t g = fr.offset + (fr.perm ? fr.perm[i] : i);
+  keys[g] = out_of_range ? kMergeNoKey : key;
+  vals[g] = g;
+}
+// points outside the 21-bit key range are not keyed by the reference and keep destination 0 = the voxel of the SMALLEST key
+__global__ void merge_fix_keys_kernel(unsigned long long* __restrict__ keys, size_t n, const unsigned long long* __restrict__ min_key) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n && keys[i] == kMergeNoKey) keys[i] = (*min_key == kMergeNoKey) ? 0ull : *min_key;
+}
+__global__ void merge_heads_kernel(const unsigned long long* __restrict__ keys, size_t n, uint32_t* __restrict__ flags) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void merge_starts_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ incl, size_t n, uint32_t* __restrict__ starts) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n && flags[i]) starts[incl[i] - 1u] = static_cast<uint32_t>(i);
+  if (i == n - 1) starts[incl[i]] = static_cast<uint32_t>(n);
+}
+__global__ void merge_sum_kernel(const MergeFrame* __restrict__ frames, int F, const uint32_t* __restrict__ sorted_vals, const uint32_t* __restrict__ starts, uint32_t num_voxels,
+                                 double* __restrict__ out_xyz, double* __restrict__ out_cov) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= num_voxels) return;
+  double sp[3] = {0.0, 0.0, 0.0}, sc[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, w = 0.0;
+  for (uint32_t k = starts[v]; k < starts[v + 1]; k++) {
+    const uint32_t g = sorted_vals[k];
+    const MergeFrame& fr = frames[merge_frame_of(frames, F, g)];
+    const uint32_t caller = g - fr.offset;
+    const size_t i = fr.inv_perm ? fr.inv_perm[caller] : caller;
+    const double x = merge_ld(fr.pts, fr.point_bytes, i), y = merge_ld(fr.pts, fr.point_bytes, fr.n_pad + i), z = merge_ld(fr.pts, fr.point_bytes, 2ull * fr.n_pad + i);
+    const double* P = fr.pose;
+#pragma unroll
+    for (int r = 0; r < 3; r++) sp[r] = __dadd_rn(sp[r], __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P[r * 4 + 0], x), __dmul_rn(P[r * 4 + 1], y)), __dmul_rn(P[r * 4 + 2], z)), P[r * 4 + 3]));
+    w = __dadd_rn(w, 1.0);
+    if (fr.covs != nullptr) {
+      double C[3][3];
+      C[0][0] = merge_ld(fr.covs, fr.cov_bytes, i);
+      C[0][1] = C[1][0] = merge_ld(fr.covs, fr.cov_bytes, fr.n_pad + i);
+      C[0][2] = C[2][0] = merge_ld(fr.covs, fr.cov_bytes, 2ull * fr.n_pad + i);
+      C[1][1] = merge_ld(fr.covs, fr.cov_bytes, 3ull * fr.n_pad + i);
+      C[1][2] = C[2][1] = merge_ld(fr.covs, fr.cov_bytes, 4ull * fr.n_pad + i);
+      C[2][2] = merge_ld(fr.covs, fr.cov_bytes, 5ull * fr.n_pad + i);
+      double T1[3][3];  // (pose * C)(r, c): coefficient sums in index order (the 4th terms of the 4x4 product are zeros)
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) T1[r][c] = __dadd_rn(__dadd_rn(__dmul_rn(P[r * 4 + 0], C[0][c]), __dmul_rn(P[r * 4 + 1], C[1][c])), __dmul_rn(P[r * 4 + 2], C[2][c]));
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          sc[r * 3 + c] = __dadd_rn(sc[r * 3 + c], __dadd_rn(__dadd_rn(__dmul_rn(T1[r][0], P[c * 4 + 0]), __dmul_rn(T1[r][1], P[c * 4 + 1])), __dmul_rn(T1[r][2], P[c * 4 + 2])));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) out_xyz[static_cast<size_t>(v) * 3 + r] = __ddiv_rn(sp[r], w);
+#pragma unroll
+  for (int k = 0; k < 9; k++) out_cov[static_cast<size_t>(v) * 9 + k] = __ddiv_rn(sc[k], w);
+}
+__global__ void merge_invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ inv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = i;
+}
+struct MinU64 {
+  __host__ __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a < b ? a : b; }
+};
 
 // load factor <= 0.25 (see b2_device.cuh: one-round-trip lookups)
 size_t bucket_count_for(size_t num_voxels) { return static_cast<size_t>(next_pow2(std::max<uint64_t>(64, 4 * static_cast<uint64_t>(num_voxels)))); }
@@ -706,6 +817,98 @@ b2_status b2_overlap(const b2_voxelmap* const* targets, size_t num_targets, cons
   B2_CUDA(cudaMemcpyAsync(&cnt, d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
   *out_overlap = static_cast<double>(cnt) / static_cast<double>(source->n);  // gaussian_voxelmap_cpu_funcs.cpp:142
+  return B2_OK;
+}
+
+b2_status b2_merge_frames(b2_ctx* ctx, const double* poses, const b2_cloud* const* frames, size_t num_frames, double downsample_resolution, double* out_points,
+                          double* out_covs, size_t* out_n) {
+  B2_REQUIRE(ctx && poses && frames && out_n && num_frames > 0, "b2_merge_frames: NULL / empty argument");
+  B2_REQUIRE(downsample_resolution > 0.0, "b2_merge_frames: downsample_resolution must be positive");
+  size_t total = 0;
+  bool have_covs = true;
+  for (size_t f = 0; f < num_frames; f++) {
+    B2_REQUIRE(frames[f] != nullptr && (frames[f]->n == 0 || frames[f]->d_points != nullptr), "error: frame %zu has no points", f);
+    B2_REQUIRE(frames[f]->ctx->device == ctx->device, "b2_merge_frames: frame %zu lives on another device", f);
+    total += frames[f]->n;
+    have_covs = have_covs && (frames[f]->n == 0 || frames[f]->d_covs != nullptr);
+  }
+  B2_REQUIRE(total < (1ull << 31), "b2_merge_frames: too many points");
+  *out_n = 0;
+  if (total == 0) return B2_OK;
+  B2_REQUIRE(out_points != nullptr && (out_covs != nullptr || !have_covs), "b2_merge_frames: output arrays are NULL");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+
+  // first_pose^-1 (rigid inverse) and the relative poses, with the CPU function's operation order
+  auto at = [&](const double* T, int r, int c) { return T[r * 4 + c]; };
+  double inv0[16] = {0};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) inv0[r * 4 + c] = at(poses, c, r);
+  for (int r = 0; r < 3; r++) inv0[r * 4 + 3] = -(inv0[r * 4 + 0] * at(poses, 0, 3) + inv0[r * 4 + 1] * at(poses, 1, 3) + inv0[r * 4 + 2] * at(poses, 2, 3));
+  inv0[15] = 1.0;
+  std::vector<MergeFrame> h(num_frames);
+  std::vector<DevBuf> inv_perms(num_frames);
+  uint32_t offset = 0;
+  for (size_t f = 0; f < num_frames; f++) {
+    const b2_cloud* c = frames[f];
+    MergeFrame& m = h[f];
+    m.pts = c->d_points, m.covs = have_covs ? c->d_covs : nullptr, m.perm = c->d_perm, m.inv_perm = nullptr;
+    m.n = static_cast<uint32_t>(c->n), m.n_pad = static_cast<uint32_t>(c->n_pad), m.offset = offset;
+    m.point_bytes = c->point_bytes, m.cov_bytes = c->cov_bytes;
+    const double* P = poses + 16 * f;
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 4; cc++) {
+        double s2 = inv0[r * 4 + 0] * at(P, 0, cc);
+        for (int k = 1; k < 4; k++) s2 += inv0[r * 4 + k] * at(P, k, cc);
+        m.rel[r * 4 + cc] = s2;
+        m.pose[r * 4 + cc] = at(P, r, cc);
+      }
+    if (c->d_perm && c->n > 0) {
+      B2_CUDA(cudaMalloc(&inv_perms[f].p, c->n * sizeof(uint32_t)));
+      merge_invert_perm_kernel<<<static_cast<unsigned>((c->n + 255) / 256), 256, 0, st>>>(c->d_perm, m.n, inv_perms[f].as<uint32_t>());
+      m.inv_perm = inv_perms[f].as<uint32_t>();
+    }
+    offset += m.n;
+  }
+  DevBuf d_frames, keys, keys2, vals, vals2, flags, incl, starts, d_min, tmp, d_xyz, d_cov;
+  const int ni = static_cast<int>(total);
+  B2_CUDA(cudaMalloc(&d_frames.p, num_frames * sizeof(MergeFrame)));
+  B2_CUDA(cudaMalloc(&keys.p, total * 8));
+  B2_CUDA(cudaMalloc(&keys2.p, total * 8));
+  B2_CUDA(cudaMalloc(&vals.p, total * 4));
+  B2_CUDA(cudaMalloc(&vals2.p, total * 4));
+  B2_CUDA(cudaMalloc(&flags.p, total * 4));
+  B2_CUDA(cudaMalloc(&incl.p, total * 4));
+  B2_CUDA(cudaMalloc(&starts.p, (total + 1) * 4));
+  B2_CUDA(cudaMalloc(&d_min.p, 8));
+  B2_CUDA(cudaMemcpyAsync(d_frames.p, h.data(), num_frames * sizeof(MergeFrame), cudaMemcpyHostToDevice, st));
+  for (size_t f = 0; f < num_frames; f++)
+    if (h[f].n) merge_keys_kernel<<<(h[f].n + 255) / 256, 256, 0, st>>>(d_frames.as<MergeFrame>(), static_cast<int>(f), 1.0 / downsample_resolution, keys.as<unsigned long long>(), vals.as<uint32_t>());
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  cub::DeviceReduce::Reduce(nullptr, t1, keys.as<unsigned long long>(), d_min.as<unsigned long long>(), ni, MinU64(), kMergeNoKey, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, t2, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), vals.as<uint32_t>(), vals2.as<uint32_t>(), ni, 0, 63, st);
+  cub::DeviceScan::InclusiveSum(nullptr, t3, flags.as<uint32_t>(), incl.as<uint32_t>(), ni, st);
+  size_t tb = std::max(t1, std::max(t2, t3));
+  B2_CUDA(cudaMalloc(&tmp.p, std::max<size_t>(tb, 16)));
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  B2_CUDA(cub::DeviceReduce::Reduce(tmp.p, tb, keys.as<unsigned long long>(), d_min.as<unsigned long long>(), ni, MinU64(), kMergeNoKey, st));
+  merge_fix_keys_kernel<<<grid, 256, 0, st>>>(keys.as<unsigned long long>(), total, d_min.as<unsigned long long>());
+  B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), vals.as<uint32_t>(), vals2.as<uint32_t>(), ni, 0, 63, st));
+  merge_heads_kernel<<<grid, 256, 0, st>>>(keys2.as<unsigned long long>(), total, flags.as<uint32_t>());
+  B2_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, flags.as<uint32_t>(), incl.as<uint32_t>(), ni, st));
+  merge_starts_kernel<<<grid, 256, 0, st>>>(flags.as<uint32_t>(), incl.as<uint32_t>(), total, starts.as<uint32_t>());
+  uint32_t num_voxels = 0;
+  B2_CUDA(cudaMemcpyAsync(&num_voxels, incl.as<uint32_t>() + (total - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  B2_CUDA(cudaMalloc(&d_xyz.p, static_cast<size_t>(num_voxels) * 3 * sizeof(double)));
+  B2_CUDA(cudaMalloc(&d_cov.p, static_cast<size_t>(num_voxels) * 9 * sizeof(double)));
+  merge_sum_kernel<<<(num_voxels + 127) / 128, 128, 0, st>>>(d_frames.as<MergeFrame>(), static_cast<int>(num_frames), vals2.as<uint32_t>(), starts.as<uint32_t>(), num_voxels, d_xyz.as<double>(),
+                                                             d_cov.as<double>());
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaMemcpyAsync(out_points, d_xyz.p, static_cast<size_t>(num_voxels) * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out_covs) B2_CUDA(cudaMemcpyAsync(out_covs, d_cov.p, static_cast<size_t>(num_voxels) * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  *out_n = num_voxels;
   return B2_OK;
 }
 

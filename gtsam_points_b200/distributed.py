@@ -158,9 +158,12 @@ class ShardedFactorSet:
         self._enter_lib()
         capi.check(capi.lib().b2_exchange_linearize(ex["h"], self.set.h if self.local_factors else None, capi.dptr(h_deltas) if self.local_factors else None, self.first, self.step))
         self._leave_lib()
-        ptr = capi.lib().b2_exchange_records(ex["h"], self.step)
         # NOTE: this view aliases the parity block of this step; a peer overwrites it when it issues step + 2
-        self.d_all = _device_view(self.torch, ptr, (self.num_global, RECORD), self.device)
+        views = ex.setdefault("views", {})
+        par = self.step & 1
+        if par not in views:  # two views in a set's lifetime (building one costs tens of microseconds)
+            views[par] = _device_view(self.torch, capi.lib().b2_exchange_records(ex["h"], self.step), (self.num_global, RECORD), self.device)
+        self.d_all = views[par]
         return self.d_all
 
     def device_barrier(self):

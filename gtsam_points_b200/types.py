@@ -226,6 +226,21 @@ def overlap_gpu(targets, source: PointCloud, Ts_target_source) -> float:
     return out.value
 
 
+def merge_frames_gpu(poses, frames, downsample_resolution: float, ctx: "Context | None" = None) -> PointCloud:
+    """merge_frames_gpu (include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:127-150): merges posed frames (poses: world <- frame
+    4x4 each) into one cloud downsampled on a voxel grid laid out in the first frame's coordinates; means of the world points and
+    of the rotated covariances, bit-identical to the CPU merge_frames.  Returns a device-resident PointCloud."""
+    ctx = ctx or frames[0].ctx
+    P = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(len(frames), 16))
+    total = sum(len(f.points) for f in frames)
+    xyz = np.zeros((max(total, 1), 3), dtype=np.float64)
+    cov = np.zeros((max(total, 1), 9), dtype=np.float64)
+    m = C.c_size_t()
+    arr = (C.c_void_p * len(frames))(*[f.h for f in frames])
+    capi.check(capi.lib().b2_merge_frames(ctx.h, capi.dptr(P), arr, len(frames), float(downsample_resolution), capi.dptr(xyz), capi.dptr(cov), C.byref(m)))
+    return PointCloud(xyz[: m.value].copy(), cov[: m.value].reshape(-1, 3, 3).copy(), ctx=ctx)
+
+
 class KdTree:
     """NearestNeighborSearch over a point set, exact 1-NN on the device."""
 

@@ -164,6 +164,14 @@ B2_API b2_status b2_voxelmap_load(b2_ctx* ctx, const char* path, b2_voxelmap** o
  * fraction of the source points p for which T_j p lies in a voxel of target j for some j (first match counts).
  * Ts_target_source: num_targets x 16 doubles (row-major 4x4). */
 B2_API b2_status b2_overlap(const b2_voxelmap* const* targets, size_t num_targets, const b2_cloud* source, const double* Ts_target_source, double* out_overlap);
+/* merge_frames_gpu (src/gtsam_points/types/gaussian_voxelmap_gpu_funcs.cu:196-330; CPU twin gaussian_voxelmap_cpu_funcs.cpp:25-113):
+ * merges num_frames posed frames (poses: num_frames x 16, row-major 4x4, world <- frame) into ONE cloud downsampled on a grid of
+ * downsample_resolution laid out in the FIRST frame's coordinates: per occupied voxel the mean of the world points and of the
+ * rotated covariances, voxels in ascending 63-bit key order (the CPU function's order and summation order: bit-identical).
+ * out_points (m x 3) / out_covs (m x 9, row-major 3x3; may be NULL if no frame has covariances) must hold one entry per input
+ * point (m <= total); *out_n = m.  Feed them to b2_cloud_create for a device-resident merged frame. */
+B2_API b2_status b2_merge_frames(b2_ctx* ctx, const double* poses, const b2_cloud* const* frames, size_t num_frames, double downsample_resolution,
+                                 double* out_points, double* out_covs, size_t* out_n);
 /* voxel_coord + lookup_voxel_index for n host points (gaussian_voxelmap_cpu.cpp:59-69); out_index[i] = id or -1 */
 B2_API b2_status b2_voxelmap_lookup(const b2_voxelmap* vm, const double* points, int point_stride, size_t n, int32_t* out_index);
 

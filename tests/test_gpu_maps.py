@@ -7,6 +7,7 @@ pytestmark = pytest.mark.gpu
 
 import golden_util
 import oracle_lib as orc
+from gtsam_points_b200 import capi
 from gtsam_points_b200 import synthetic as syn
 
 
@@ -121,3 +122,23 @@ def test_overlap_gpu_equals_cpu_overlap(g, gold):
         assert g.overlap_gpu(vm, src, T) == ovm.overlap(osrc, T)
         Ts = np.stack([T, syn.random_pose(rng, 0.3, 3.0)])
         assert g.overlap_gpu([vm, vm2], src, Ts) == orc.overlap_multi([ovm, ovm2], osrc, Ts)
+
+
+def test_merge_frames_gpu_equals_cpu_merge_frames(g, gold):
+    """merge_frames_gpu vs merge_frames (gaussian_voxelmap_cpu_funcs.cpp:25-113): same voxels in the same (key) order, means of
+    world points and rotated covariances BIT-identical (same summation order), Morton-reordered and caller-order storage alike;
+    the merged cloud is a usable frame (src/test/test_voxelmap.cpp:108-131 merges frames and checks the overlap with the inputs)."""
+    tp, tc, sp, sc = gold["target_points"], gold["target_covs"], gold["source_points"], gold["source_covs"]
+    poses = np.stack([gold["T_target"], gold["T_source_gt"]])
+    for flags in (capi.B2_CLOUD_DEFAULT, capi.B2_CLOUD_NO_REORDER):
+        frames = [g.PointCloud(tp, tc, flags=flags), g.PointCloud(sp, sc, flags=flags)]
+        for res in (0.5, 0.2):
+            merged = g.merge_frames_gpu(poses, frames, res)
+            xyz, cov = orc.merge_frames(poses, [orc.Cloud(tp, tc), orc.Cloud(sp, sc)], res)
+            assert len(merged.points) == len(xyz) and len(xyz) < len(tp) + len(sp)
+            assert np.array_equal(merged.points, xyz)
+            assert np.array_equal(merged.covs, cov.reshape(-1, 3, 3))
+    # every input point lies in a voxel of a map built from the merged frame at the same resolution-ish scale
+    vm = g.GaussianVoxelMapGPU(1.0)
+    vm.insert(merged)
+    assert g.overlap_gpu(vm, g.PointCloud(tp, tc), poses[0]) > 0.9
