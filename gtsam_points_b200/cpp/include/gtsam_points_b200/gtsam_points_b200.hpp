@@ -209,13 +209,17 @@ public:
 
   double voxel_resolution() const override { return resolution_; }
 
-  // GaussianVoxelMap::insert(const PointCloud&): one-shot on the GPU (types/gaussian_voxelmap_gpu.hpp:63)
+  // GaussianVoxelMap::insert(const PointCloud&).  Unlike the reference's GPU map (one-shot, types/gaussian_voxelmap_gpu.hpp:63)
+  // this is the CPU map's INCREMENTAL insert (ann/impl/incremental_voxelmap_impl.hpp:31-68): repeated calls extend the map,
+  // ids stay first-touch, voxels untouched for lru_horizon inserts are dropped every lru_clear_cycle inserts.
   void insert(const double* points, int point_stride, const double* covs, int cov_stride, std::size_t n) {
-    if (vm_) {
-      std::cerr << "error: incremental insertion is not supported for GPU voxelmaps" << std::endl;
-      abort();
-    }
-    check(b2_voxelmap_create_from_points(ctx_->get(), resolution_, points, point_stride, covs, cov_stride, n, &vm_), "b2_voxelmap_create_from_points");
+    if (!vm_) check(b2_voxelmap_create(ctx_->get(), resolution_, &vm_), "b2_voxelmap_create");
+    check(b2_voxelmap_insert(vm_, points, point_stride, covs, cov_stride, n), "b2_voxelmap_insert");
+  }
+  // IncrementalVoxelMap::set_lru_horizon / set_lru_clear_cycle (ann/incremental_voxelmap.hpp:41-46); defaults 10 / 10
+  void set_lru(std::size_t lru_horizon, std::size_t lru_clear_cycle) {
+    if (!vm_) check(b2_voxelmap_create(ctx_->get(), resolution_, &vm_), "b2_voxelmap_create");
+    check(b2_voxelmap_set_lru(vm_, lru_horizon, lru_clear_cycle), "b2_voxelmap_set_lru");
   }
   template <typename Frame>
   void insert(const Frame& frame) {  // frame: the reference's PointCloud shape

@@ -152,6 +152,14 @@ int main(int argc, char** argv) {
   auto voxels = std::make_shared<GaussianVoxelMapGPU>(res[0]);
   voxels->insert(*target_frame);
   GaussianVoxelMap::ConstPtr voxels_base = voxels;  // factors take the abstract map, like the reference
+  {
+    // incremental insert (the CPU map's semantics): two halves give the voxels of the whole
+    auto halves = std::make_shared<GaussianVoxelMapGPU>(res[0]);
+    const std::size_t h = nt / 2;
+    halves->insert(tp.data(), 4, tc.data(), 16, h);
+    halves->insert(tp.data() + 4 * h, 4, tc.data() + 16 * h, 16, nt - h);
+    if (halves->num_voxels() != voxels->num_voxels() || halves->num_voxels() == 0) fails++;
+  }
 
   auto vgicp = std::make_shared<IntegratedVGICPFactor>(Key(0), Key(1), voxels_base, source_c);
   auto gicp = std::make_shared<IntegratedGICPFactor>(Key(0), Key(1), target_c, source_c);
