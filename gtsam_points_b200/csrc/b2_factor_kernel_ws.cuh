@@ -144,8 +144,20 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
   // ---- last CTA of this factor ----
   __threadfence();
   {
+    // Lane l of warp w sums accumulator l over slots w, w + kC, ... in slot order.  The loads of 8 slots are issued together
+    // (they are independent L2 round trips: one after the other they made this CTA the straggler of the whole launch -- 19
+    // dependent ~800-cycle trips per warp for a 148-CTA factor); the additions keep the sequential order, so the bits do too.
     double s = 0.0;
-    for (uint32_t sl = warp; sl < d.num_slots[MODE]; sl += kC) s += __ldcg(&partials[(static_cast<size_t>(d.slot_begin[MODE]) + sl) * kAcc + lane]);
+    const uint32_t ns = d.num_slots[MODE];
+    const double* __restrict__ base = partials + static_cast<size_t>(d.slot_begin[MODE]) * kAcc + lane;
+    for (uint32_t sl = warp; sl < ns; sl += 8 * kC) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = (sl + j * kC < ns) ? __ldcg(base + static_cast<size_t>(sl + j * kC) * kAcc) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (sl + j * kC < ns) s += v[j];
+    }
     sh.red[warp][lane] = s;
   }
   consumer_barrier();
@@ -158,11 +170,15 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
   if (ctid == 0) counters[d.out_index] = 0u;  // re-arm for the next launch
   consumer_barrier();
 
+  // results in mapped host memory / peer memory always come with a completion signal: only then the fence must be system-wide
+  const bool system_scope = sig.flag != nullptr || sig.n_peers > 0;
   if (MODE == MODE_ERROR) {
     if (ctid == 0) {
       out[d.out_index] = sh.tot[27];
-      __threadfence_system();  // `out` may be mapped host memory
-      signal_done(sig);
+      if (system_scope) {
+        __threadfence_system();  // `out` may be mapped host memory
+        signal_done(sig);
+      }
     }
     consumer_barrier();
     return;
@@ -175,7 +191,7 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
     // remember the linearization point with the factor (error-only launches of ANY set read it back)
     d.lin_pose[ctid - 100] = pose_lin[ctid - 100];
   }
-  __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
+  if (system_scope) __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
   consumer_barrier();
   if (sig.n_peers > 1) {
     // multi-GPU exchange fused into the epilogue: copy the finished record into the same slot of every peer's buffer

@@ -88,7 +88,9 @@ __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
   const unsigned int prev = atomicAdd(sig.counter, 1u);
   if (prev == sig.total - 1u) {  // every factor of this call is done: re-arm the counter, publish the sequence number
     *sig.counter = 0u;
-    __threadfence_system();
+    // acquire side of the counter chain: the other factors' CTAs fenced their records before their atomicAdd; with a single
+    // factor the caller's own fence (just before this call) already ordered the record before the flag
+    if (sig.total > 1u || sig.n_peers > 0) __threadfence_system();
     if (sig.n_peers > 0) {
       for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
       if (sig.wait_in_kernel) {
