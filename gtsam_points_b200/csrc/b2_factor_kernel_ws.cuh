@@ -150,12 +150,13 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
     double s = 0.0;
     const uint32_t ns = d.num_slots[MODE];
     const double* __restrict__ base = partials + static_cast<size_t>(d.slot_begin[MODE]) * kAcc + lane;
-    for (uint32_t sl = warp; sl < ns; sl += 8 * kC) {
-      double v[8];
+    constexpr int kInFlight = 24;  // one round trip covers 24 * kC slots (a 148-CTA factor: 19 slots per warp at kC = 8)
+    for (uint32_t sl = warp; sl < ns; sl += kInFlight * kC) {
+      double v[kInFlight];
 #pragma unroll
-      for (int j = 0; j < 8; j++) v[j] = (sl + j * kC < ns) ? __ldcg(base + static_cast<size_t>(sl + j * kC) * kAcc) : 0.0;
+      for (int j = 0; j < kInFlight; j++) v[j] = (sl + j * kC < ns) ? __ldcg(base + static_cast<size_t>(sl + j * kC) * kAcc) : 0.0;
 #pragma unroll
-      for (int j = 0; j < 8; j++)
+      for (int j = 0; j < kInFlight; j++)
         if (sl + j * kC < ns) s += v[j];
     }
     sh.red[warp][lane] = s;
@@ -608,9 +609,11 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
       }
 #ifdef B2_WS_TIMING
       if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 2], globaltimer());
-      if (lane == 0) atomicMin(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());
 #endif
       flush_factor<MODE>(sh, acc, ctid, partials, counters, out, SINGLE ? pose.m : (poses_lin + static_cast<size_t>(sh.desc.out_index) * 16), sig);
+#ifdef B2_WS_TIMING
+      if (lane == 0) atomicMax(&g_cta_times[blockIdx.x * 4 + 3], globaltimer());  // flush (and, in the factor's last CTA, the epilogue) done
+#endif
       tile = run_end;
     }
   }

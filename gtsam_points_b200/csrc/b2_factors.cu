@@ -85,9 +85,11 @@ struct PoseArg {
 // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
 __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
   if (sig.flag == nullptr) return;
-  const unsigned int prev = atomicAdd(sig.counter, 1u);
+  // a call of ONE factor needs no counter: its only finisher publishes directly (saves a device atomic's round trip on the
+  // latency path of the headline call)
+  const unsigned int prev = sig.total == 1u ? 0u : atomicAdd(sig.counter, 1u);
   if (prev == sig.total - 1u) {  // every factor of this call is done: re-arm the counter, publish the sequence number
-    *sig.counter = 0u;
+    if (sig.total != 1u) *sig.counter = 0u;
     // acquire side of the counter chain: the other factors' CTAs fenced their records before their atomicAdd; with a single
     // factor the caller's own fence (just before this call) already ordered the record before the flag
     if (sig.total > 1u || sig.n_peers > 0) __threadfence_system();
@@ -214,8 +216,10 @@ __device__ __forceinline__ void epilogue_store(double* __restrict__ rec, const d
   if (tid < 36) {
     const int i = tid / 6, j = tid % 6;
     double ht = 0.0, hs = 0.0, hts = 0.0;
+#pragma unroll
     for (int a = 0; a < 6; a++) {
       double xa = 0.0, da = 0.0;  // (A X)[a][j], (A D)[a][j]
+#pragma unroll
       for (int b = 0; b < 6; b++) {
         xa += A[a * 6 + b] * X[b * 6 + j];
         da += A[a * 6 + b] * D[b * 6 + j];
@@ -230,6 +234,7 @@ __device__ __forceinline__ void epilogue_store(double* __restrict__ rec, const d
   } else if (tid >= 64 && tid < 70) {
     const int i = tid - 64;
     double bt = 0.0, bs = 0.0;
+#pragma unroll
     for (int a = 0; a < 6; a++) {
       const double ca = tot[21 + a];
       bt += X[a * 6 + i] * ca;
@@ -1402,6 +1407,17 @@ b2_status b2_exchange_wait(b2_ctx* ctx, const unsigned int* d_flags, int n_peers
   B2_CUDA(cudaGetLastError());
   return B2_OK;
 }
+
+#ifdef B2_WS_TIMING
+// development aid (scripts/cta_times.py; never in the production build): per-CTA {start, probe warps done, accumulate warps done,
+// flush done} timestamps (ns) of the VGICP kernel's launches since the previous call; resets them
+__attribute__((visibility("default"))) void b2_debug_cta_times(unsigned long long* out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, b2::ws::g_cta_times, static_cast<size_t>(n) * 4 * sizeof(unsigned long long));
+  static unsigned long long zeros[1024 * 4];
+  cudaMemcpyToSymbol(b2::ws::g_cta_times, zeros, sizeof(zeros));
+}
+#endif
 
 // ---- exchange objects: peer-mapped result blocks through CUDA IPC / peer access, no framework above the ABI ------------------
 }  // extern "C"

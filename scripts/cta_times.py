@@ -24,6 +24,6 @@ for k in range(6):
     fn(buf.ctypes.data, 148)
     t = buf.reshape(148, 4).astype(np.int64)
     t0 = t[:, 0].min()
-    start, pend, aend, afirst = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3, (t[:, 3] - t0) / 1e3
+    start, pend, aend, fend = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3, (t[:, 3] - t0) / 1e3
     q = lambda a: " ".join(f"{v:6.1f}" for v in np.percentile(a, [0, 10, 50, 90, 100]))
-    print(f"run {k}: CTA start us [min p10 p50 p90 max] {q(start)} | probe done {q(pend)} | accumulate done {q(aend)} | per-CTA busy {q(aend - start)}")
+    print(f"run {k}: CTA start us [min p10 p50 p90 max] {q(start)} | probe done {q(pend)} | accumulate done {q(aend)} | flush done {q(fend)} | flush - accumulate {q(fend - aend)}")
