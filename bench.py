@@ -253,14 +253,17 @@ def run_reference(args):
     tp, tc, sp, sc = make_inputs(0)
     steps = max(args.steps, 10)  # median of >= 10 calls
     poses = make_poses(0, steps + args.warmup)
+    native = os.environ.get("B2_ORACLE_NATIVE") == "1"
+    # the -march=native child runs FIRST: afterwards this process's own OpenMP team exists and (OMP_WAIT_POLICY=active) spins
+    # on the cores between parallel regions, which would steal them from the child
+    native_value = time_cpu_native(steps, args.warmup) if (not native and not args.no_native) else None
     times, threads = time_cpu(tp, tc, sp, sc, poses, args.warmup, steps)
     value = cpu_value(times)
-    native = os.environ.get("B2_ORACLE_NATIVE") == "1"
     sample = (f"median of {steps} linearize() calls of the full 1M-pt workload after {args.warmup} warm-up, one pinned OpenMP thread per physical core"
               + (", -march=native build" if native else ", reference default flags (-O3, no -march=native)"))
     cpu_baseline = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "min_ms": 1e3 * float(np.min(times)), "max_ms": 1e3 * float(np.max(times))}
-    if not native and not args.no_native:
-        cpu_baseline["native_value"] = time_cpu_native(steps, args.warmup)
+    if native_value is not None:
+        cpu_baseline["native_value"] = native_value
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -316,6 +319,9 @@ def run_gpu(args):
     K, W = args.steps, args.warmup
     dp = C.POINTER(C.c_double)
     L = capi.lib()
+    # the -march=native CPU child runs before this process creates its own OpenMP team (parity check / cpu_baseline below): with
+    # OMP_WAIT_POLICY=active that team spins on the cores between parallel regions and would steal them from the child
+    native_cpu_value = time_cpu_native(10, 2) if (world == 1 and not args.no_cpu_baseline and not args.no_native) else None
 
     def barrier():
         if world > 1:
@@ -542,7 +548,7 @@ def run_gpu(args):
                 "sample": f"median of {cs} linearize() calls of the full 1M-pt workload after {cw} warm-up, one pinned OpenMP thread per physical core, reference default flags",
                 "min_ms": 1e3 * float(np.min(times)),
                 "max_ms": 1e3 * float(np.max(times)),
-                "native_value": time_cpu_native(cs, cw),  # same code, -march=native (the reference's optional BUILD_WITH_MARCH_NATIVE)
+                "native_value": native_cpu_value,  # same code, -march=native (the reference's optional BUILD_WITH_MARCH_NATIVE); timed first
                 "host": host_info(),
                 "single_thread_value": time_cpu_single_thread(tp, tc, sp, sc, poses[0]),  # the reference's default num_threads = 1
             }
