@@ -108,6 +108,7 @@ SIGNATURES = {
     "b2_exchange_import": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ubyte)]),
     "b2_exchange_enable_peer": (C.c_int, [_vp, C.c_int, _vp]),
     "b2_exchange_linearize": (C.c_int, [_vp, _vp, _dp, C.c_size_t, C.c_uint]),
+    "b2_exchange_linearize_host": (C.c_int, [_vp, _vp, _dp, C.c_size_t, C.c_uint, _dp]),
     "b2_exchange_records": (_vp, [_vp, C.c_uint]),
     "b2_exchange_barrier": (C.c_int, [_vp]),
     "b2_factor_set_launch_count": (C.c_uint64, [_vp]),

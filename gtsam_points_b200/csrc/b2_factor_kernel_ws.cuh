@@ -192,7 +192,9 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
     // remember the linearization point with the factor (error-only launches of ANY set read it back)
     d.lin_pose[ctid - 100] = pose_lin[ctid - 100];
   }
-  if (system_scope) __threadfence_system();  // `out` may be mapped host memory (zero-copy host API)
+  // `out` may be mapped host memory (zero-copy host API): fence at system scope before the completion signal.  With peers, `out`
+  // is this GPU's own device block and ONE system fence after the peer copies below covers everything that leaves the GPU
+  if (system_scope && sig.n_peers <= 1) __threadfence_system();
   consumer_barrier();
   if (sig.n_peers > 1) {
     // multi-GPU exchange fused into the epilogue: copy the finished record into the same slot of every peer's buffer
@@ -205,7 +207,19 @@ __device__ __forceinline__ void flush_factor(Shared& sh, double (&v)[kAcc], int 
     __threadfence_system();
     consumer_barrier();
   }
-  if (ctid == 0) signal_done(sig);  // every writer of this record fenced before the barrier
+  if (sig.mirror == nullptr) {
+    if (ctid == 0) signal_done(sig);  // every writer of this record fenced before the barrier
+  } else {
+    // exchange step with host delivery: the CTA that completes the call (and waited for the peers) copies every rank's records
+    // from this GPU's block to mapped host memory, then raises the host's completion word
+    if (ctid == 0) sh.flag = signal_done(sig) ? 1 : 0;
+    consumer_barrier();
+    if (sh.flag) {
+      mirror_to_host(sig, ctid, kCT);
+      consumer_barrier();
+      if (ctid == 0) *sig.mirror_flag = sig.mirror_seq;
+    }
+  }
   (void)kCT;
 }
 

@@ -57,6 +57,14 @@ struct DoneSignal {
   int wait_in_kernel;  // the signalling thread also waits until every rank's flag in THIS GPU's array shows seq: the launch completes = the exchange completed
   double* peer_out[kMaxPeers];          // same offset as `out` of the launch, in each peer's buffer (entry my_rank unused)
   unsigned int* peer_flag[kMaxPeers];   // each GPU's flag array [n_peers]
+  // Host delivery of an exchange step (b2_exchange_linearize_host): once every rank's flag has arrived, the CTA that waited copies
+  // ALL records of the step from this GPU's block into pinned mapped host memory and then raises a mapped completion word: the
+  // host gets every rank's records without a copy operation or a stream synchronisation.  mirror == nullptr: unused.
+  const double* mirror_src;
+  double* mirror;
+  unsigned int mirror_doubles;
+  unsigned int mirror_seq;              // value the host waits for in *mirror_flag
+  volatile unsigned int* mirror_flag;
 };
 
 // stride S ~ n / golden ratio with gcd(S, n) == 1: v -> (v * S) mod n is a permutation that spreads any run of v evenly
@@ -83,8 +91,9 @@ struct PoseArg {
 };
 
 // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
-__device__ __forceinline__ void signal_done(const DoneSignal& sig) {
-  if (sig.flag == nullptr) return;
+// returns true iff this caller completed the whole call (and, with wait_in_kernel, has seen every rank's flag)
+__device__ __forceinline__ bool signal_done(const DoneSignal& sig) {
+  if (sig.flag == nullptr) return false;
   // a call of ONE factor needs no counter: its only finisher publishes directly (saves a device atomic's round trip on the
   // latency path of the headline call)
   const unsigned int prev = sig.total == 1u ? 0u : atomicAdd(sig.counter, 1u);
@@ -92,7 +101,7 @@ __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
     if (sig.total != 1u) *sig.counter = 0u;
     // acquire side of the counter chain: the other factors' CTAs fenced their records before their atomicAdd; with a single
     // factor the caller's own fence (just before this call) already ordered the record before the flag
-    if (sig.total > 1u || sig.n_peers > 0) __threadfence_system();
+    if (sig.total > 1u) __threadfence_system();
     if (sig.n_peers > 0) {
       for (int p = 0; p < sig.n_peers; p++) *reinterpret_cast<volatile unsigned int*>(sig.peer_flag[p] + sig.my_rank) = sig.seq;  // every GPU, own included
       if (sig.wait_in_kernel) {
@@ -111,7 +120,15 @@ __device__ __forceinline__ void signal_done(const DoneSignal& sig) {
     } else {
       *sig.flag = sig.seq;
     }
+    return true;
   }
+  return false;
+}
+
+// all `nthreads` threads of the CTA whose thread 0 got `true` from signal_done: copy the step's records to the host mirror
+__device__ __forceinline__ void mirror_to_host(const DoneSignal& sig, int tid, int nthreads) {
+  for (unsigned int i = tid; i < sig.mirror_doubles; i += nthreads) sig.mirror[i] = __ldcg(sig.mirror_src + i);
+  __threadfence_system();
 }
 
 struct FactorDesc {
@@ -1539,7 +1556,26 @@ b2_status b2_exchange_barrier(b2_exchange* ex) {
 
 const double* b2_exchange_records(const b2_exchange* ex, unsigned int step) { return ex ? ex->d_block + (step & 1u) * ex->rec_doubles() : nullptr; }
 
+namespace {
+__global__ void mirror_kernel(DoneSignal sig) {
+  mirror_to_host(sig, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) *sig.mirror_flag = sig.mirror_seq;
+}
+b2_status exchange_linearize_impl(b2_exchange* ex, b2_factor_set* s, const double* deltas, size_t first_slot, unsigned int step, double* out_host);
+}  // namespace
+
 b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* s, const double* deltas, size_t first_slot, unsigned int step) {
+  return exchange_linearize_impl(ex, s, deltas, first_slot, step, nullptr);
+}
+
+b2_status b2_exchange_linearize_host(b2_exchange* ex, b2_factor_set* s, const double* deltas, size_t first_slot, unsigned int step, double* out_records) {
+  B2_REQUIRE(out_records != nullptr, "b2_exchange_linearize_host: out_records is NULL");
+  return exchange_linearize_impl(ex, s, deltas, first_slot, step, out_records);
+}
+
+namespace {
+b2_status exchange_linearize_impl(b2_exchange* ex, b2_factor_set* s, const double* deltas, size_t first_slot, unsigned int step, double* out_host) {
   B2_REQUIRE(ex != nullptr, "b2_exchange_linearize: exchange is NULL");
   B2_REQUIRE(step != 0u, "b2_exchange_linearize: step starts at 1");
   for (int p = 0; p < ex->n; p++) B2_REQUIRE(ex->peer_block[p] != nullptr, "b2_exchange_linearize: rank %d has not been imported", p);
@@ -1557,11 +1593,32 @@ b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* s, const double*
     sig.peer_out[p] = ex->peer_block[p] + par * ex->rec_doubles() + first_slot * B2_LINEARIZED_DOUBLES;
     sig.peer_flag[p] = reinterpret_cast<unsigned int*>(ex->peer_block[p] + 2 * ex->rec_doubles()) + par * 8;
   }
+  unsigned int host_seq = 0;
+  const size_t mirror_bytes = ex->rec_doubles() * sizeof(double);
+  if (out_host != nullptr) {
+    // every rank's records of this step are delivered to pinned mapped host memory by the kernel that waited for them
+    B2_TRY(ex->ctx->ensure_stage(mirror_bytes, 0));
+    double* d_mirror = nullptr;
+    B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_mirror), ex->ctx->h_stage, 0));
+    sig.mirror_src = ex->d_block + par * ex->rec_doubles();
+    sig.mirror = d_mirror;
+    sig.mirror_doubles = static_cast<unsigned int>(ex->rec_doubles());
+    sig.mirror_flag = ex->ctx->d_done_flag;
+    host_seq = ++ex->ctx->done_seq;
+    sig.mirror_seq = host_seq;
+  }
+  auto deliver = [&]() -> b2_status {
+    if (out_host == nullptr) return B2_OK;
+    B2_TRY(wait_done(ex->ctx, host_seq));
+    std::memcpy(out_host, ex->ctx->h_stage, mirror_bytes);
+    return B2_OK;
+  };
   if (F == 0) {  // nothing to linearize on this rank: still take part (raise, then wait)
     raise_flags_kernel<<<1, 32, 0, ex->ctx->stream>>>(sig);
     wait_flags_kernel<<<1, 32, 0, ex->ctx->stream>>>(sig.peer_flag[ex->rank], ex->n, step);
+    if (out_host != nullptr) mirror_kernel<<<1, 256, 0, ex->ctx->stream>>>(sig);
     B2_CUDA(cudaGetLastError());
-    return B2_OK;
+    return deliver();
   }
   B2_REQUIRE(s->ctx == ex->ctx, "b2_exchange_linearize: set and exchange live on different contexts");
   sig.counter = s->ctx->d_done_counter;
@@ -1580,8 +1637,9 @@ b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* s, const double*
     s->factors[i]->linearized = true;
     std::memcpy(s->factors[i]->lin_delta, deltas + i * 16, 16 * sizeof(double));
   }
-  return B2_OK;
+  return deliver();
 }
+}  // namespace
 
 b2_status b2_factor_set_linearize(b2_factor_set* s, const double* deltas, b2_linearized* out) {
   B2_REQUIRE(s && deltas && out, "b2_factor_set_linearize: NULL argument");

@@ -202,6 +202,16 @@ class ShardedFactorSet:
     # -- end-to-end step: poses from the host, all records back on the host ---------------------------------------
     def linearize(self, deltas_local: np.ndarray) -> np.ndarray:
         torch = self.torch
+        if self.exchange is not None:
+            # ONE call: launch + peer stores + in-kernel wait + the kernel's own copy of every rank's records into mapped host memory
+            ex = self.exchange
+            self.step += 1
+            hd = np.ascontiguousarray(deltas_local, dtype=np.float64).reshape(-1, 16) if self.local_factors else None
+            out = ex.setdefault("h_out", np.zeros((self.num_global, RECORD), dtype=np.float64))
+            self._enter_lib()
+            capi.check(capi.lib().b2_exchange_linearize_host(ex["h"], self.set.h if self.local_factors else None, capi.dptr(hd) if self.local_factors else None, self.first, self.step, capi.dptr(out)))
+            self._leave_lib()
+            return out
         hd = None
         if self.local_factors:
             hd = np.ascontiguousarray(deltas_local, dtype=np.float64).reshape(-1, 16)

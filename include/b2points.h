@@ -306,6 +306,11 @@ B2_API b2_status b2_exchange_enable_peer(b2_exchange* ex, int peer_rank, const b
 /* deltas: HOST poses of the set's factors (F x 16), or NULL for a rank that owns no factor in this step (set may then be NULL) */
 B2_API b2_status b2_exchange_linearize(b2_exchange* ex, b2_factor_set* set, const double* deltas, size_t first_slot, unsigned int step);
 /* device pointer to the [num_records x 128] block of `step` (valid until step + 2 is issued) */
+/* Same step with HOST delivery: besides the device block, all num_records records of the step are written to out_records
+ * (host, num_records x 128 doubles) -- the CTA that waited for the peers' flags copies them into pinned mapped memory and raises a
+ * mapped completion word the call spins on: one launch, no copy operation, no stream synchronisation.  Returns when they are in. */
+B2_API b2_status b2_exchange_linearize_host(b2_exchange* ex, b2_factor_set* set, const double* deltas, size_t first_slot, unsigned int step,
+                                            double* out_records);
 B2_API const double* b2_exchange_records(const b2_exchange* ex, unsigned int step);
 /* Stream-ordered rendezvous of the exchange's GPUs (one tiny kernel on the context's stream: raise a word on every GPU, wait for
  * every rank's word): work enqueued after it starts on all GPUs within a few microseconds of each other, whatever the skew

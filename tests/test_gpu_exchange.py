@@ -58,5 +58,31 @@ def test_exchange_delivers_every_rank_its_peers_records():
             capi.check(L.b2_factor_linearize(factors[r].h, capi.dptr(deltas[r]), capi.dptr(ref)))
             assert np.array_equal(blocks[0][r], ref)  # and it is exactly what a local linearize returns
             assert ref[121] > 1000
+    # host delivery (b2_exchange_linearize_host): the call returns with every rank's records in host memory; it blocks until
+    # the peers have launched too, so the two ranks of this single-process test call it from two threads (ctypes drops the GIL)
+    import threading
+
+    for step in range(5, 8):
+        deltas = [np.ascontiguousarray(syn.random_pose(rng, 0.01, 0.1).reshape(1, 16)) for _ in range(world)]
+        outs = [np.zeros((world, capi.B2_LINEARIZED_DOUBLES)) for _ in range(world)]
+        errs = []
+
+        def run(r):
+            try:
+                capi.check(L.b2_exchange_linearize_host(exs[r], sets[r].h, capi.dptr(deltas[r]), r, step, capi.dptr(outs[r])))
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=60)
+        assert not errs and not any(t.is_alive() for t in threads)
+        assert np.array_equal(outs[0], outs[1])
+        for r in range(world):
+            ref = np.zeros(capi.B2_LINEARIZED_DOUBLES)
+            capi.check(L.b2_factor_linearize(factors[r].h, capi.dptr(deltas[r]), capi.dptr(ref)))
+            assert np.array_equal(outs[0][r], ref)
     for h in exs:
         capi.check(L.b2_exchange_destroy(h))
