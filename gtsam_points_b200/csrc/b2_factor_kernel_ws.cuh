@@ -299,7 +299,7 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     uint32_t tail = 0u, run = 0u;
     uint32_t tile = tile_lo;
     while (tile < tile_hi) {
-      const FactorDesc* __restrict__ dg = descs + (SINGLE ? 0u : __ldg(tile_factor + tile));
+      const FactorDesc* __restrict__ dg = SINGLE ? &pose.desc : descs + __ldg(tile_factor + tile);  // SINGLE: kernel-parameter space
       const uint32_t n = dg->n;
       const size_t n_pad = dg->n_pad;
       const uint32_t f_tile_begin = dg->tile_begin;
@@ -504,7 +504,8 @@ factor_kernel(const FactorDesc* __restrict__ descs, const uint32_t* __restrict__
     while (tile < tile_hi) {
       const uint32_t f = SINGLE ? 0u : __ldg(tile_factor + tile);
       consumer_barrier();  // previous flush is done with sh.desc
-      if (ctid < static_cast<int>(sizeof(FactorDesc) / 4)) reinterpret_cast<uint32_t*>(&sh.desc)[ctid] = __ldg(reinterpret_cast<const uint32_t*>(descs + f) + ctid);
+      if (ctid < static_cast<int>(sizeof(FactorDesc) / 4))
+        reinterpret_cast<uint32_t*>(&sh.desc)[ctid] = SINGLE ? reinterpret_cast<const uint32_t*>(&pose.desc)[ctid] : __ldg(reinterpret_cast<const uint32_t*>(descs + f) + ctid);
       consumer_barrier();
       const FactorDesc& d = sh.desc;
       if (ctid < 21) {

@@ -84,12 +84,6 @@ inline uint32_t golden_stride(uint32_t n) {
   return s % n == 0u ? 1u : s % n;
 }
 
-// Pose of a single-factor launch, passed BY VALUE as a kernel parameter (row-major 4x4): the arithmetic takes it as
-// constant-bank operands and the kernel reads nothing from host memory on its way in.
-struct PoseArg {
-  double m[16];
-};
-
 // called by ONE thread of the CTA that finished a factor, after that factor's results were fenced at system scope
 // returns true iff this caller completed the whole call (and, with wait_in_kernel, has seen every rank's flag)
 __device__ __forceinline__ bool signal_done(const DoneSignal& sig) {
@@ -158,6 +152,14 @@ struct FactorDesc {
   uint32_t out_index;      // index of the factor in its set (pose / result / counter)
   uint32_t cta_first[2];   // per mode: first CTA whose (contiguous) tile range touches this factor; slot = blockIdx.x - cta_first
   uint32_t perm_stride;    // virtual -> physical tile permutation within the factor: (v * perm_stride) mod num_tiles
+};
+
+// Single-factor launches pass the pose (row-major 4x4) AND the factor's descriptor BY VALUE as a kernel parameter: the arithmetic
+// takes the pose as constant-bank operands, the descriptor costs no dependent (cold) global load at kernel start, and the kernel
+// reads nothing from host memory on its way in.
+struct PoseArg {
+  double m[16];
+  FactorDesc desc;  // valid for single-factor launches (copy of the set's only descriptor)
 };
 
 __device__ __forceinline__ double ldv(const float* p, size_t i) { return static_cast<double>(__ldg(p + i)); }
@@ -874,7 +876,9 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
   cudaStream_t st = s->ctx->stream;
   PoseArg pa{};
   const bool single = h_pose != nullptr && s->factors.size() == 1 && s->groups.size() == 1 && s->groups[0].fn_single[mode] != nullptr;
-  if (single) std::memcpy(pa.m, h_pose, sizeof(pa.m));
+  if (single) {
+    std::memcpy(pa.m, h_pose, sizeof(pa.m));
+  }
   for (auto& g : s->groups) {
     // tuning setters called after the set was built (set_max_correspondence_distance) and voxel maps that grew since
     // (b2_voxelmap_insert): refresh the device descriptors, stream-ordered before the launch -- like the reference, a new
@@ -897,6 +901,7 @@ b2_status launch_groups(b2_factor_set* s, int mode, const double* d_lin, const d
         g.vm_gen[k] = vgen;
       }
     }
+    if (single) pa.desc = g.h_descs[0];  // after the refresh above: the by-value copy the kernel works from
     if (mode == MODE_LINEARIZE && g.probe != nullptr) {
       (single ? g.probe_single : g.probe)<<<g.num_tiles, kernel_shape(g.kind, g.pb, g.cb).tile, 0, st>>>(g.d_descs, g.d_tile_factor, d_lin, pa, d_frozen);
       s->launches++;
