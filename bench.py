@@ -303,6 +303,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        try:
+            os.sched_setaffinity(0, AFFINITY)  # whatever an inherited OMP_PROC_BIND did to the main thread when libgomp was loaded
+        except OSError:
+            pass
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -520,9 +525,8 @@ def run_gpu(args):
         alg_bytes = N_SOURCE * (12 + 36) + NB_alg * 16 + V * (12 + 36 + 4) + 992
         achieved = alg_bytes / (kern_ms_mean * 1e-3) / 1e9
         # ---- untimed parity check of the headline workload against the CPU oracle (rank 0; indices bit-exact, H / b 1e-9) ----
-        # (runs AFTER every timed loop: the oracle's OpenMP team keeps spinning on all cores afterwards -- OMP_WAIT_POLICY=active, as
-        # the CPU arm wants it -- and would starve the other ranks' host threads during the end-to-end loop: measured 33 ms per step
-        # at 8 ranks with the check in front of it)
+        # (runs AFTER every timed loop: with OMP_WAIT_POLICY=active -- as the CPU arm wants it at N = 1 -- the oracle's OpenMP team keeps
+        # spinning on all cores afterwards and would compete with the host threads of the end-to-end loop)
         parity = None
         if rank == 0 and not args.no_cpu_baseline:
             import oracle_lib as orc
@@ -619,7 +623,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    pin_openmp_env()
+    # Thread pinning is for the process that times the CPU oracle: the reference arm, or the single-process CUDA arm (cpu_baseline).
+    # NOT for the ranks of a multi-GPU run: with OMP_PROC_BIND set, libgomp binds every process's MAIN thread to the first place
+    # when it is loaded, i.e. all ranks to the same core -- two ranks still fit its two hardware threads, eight take turns in
+    # scheduler quanta (measured: 31 ms per end-to-end step at 8 ranks, 92 us at 2).
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" or world == 1:
+        pin_openmp_env()
     if args.impl == "reference":
         run_reference(args)
     else:
