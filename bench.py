@@ -403,6 +403,8 @@ def run_gpu(args):
             def dev_step(pose):
                 sset.linearize_device(pose)  # one launch: linearize + peer stores of the records + in-kernel flag wait
         dev_total_ms, step_ms = time_steps(dev_step, poses_c, W, K, sset.device_barrier)
+        # launches of THIS library's kernels inside the timed region: (warm-up + timed) steps launched equally many, the timed share is K of them
+        launches_dev = (sset.set.launch_count() - launches0) * K // (K + W)
         rec = sset.d_all.cpu().numpy().copy()
         exchange_path = "peer stores in the kernel epilogue (NVLink) + in-kernel flag wait (b2_exchange, CUDA IPC)" if sset.exchange is not None else "ONE all-reduce of [N x 128] f64 (NCCL)"
         if world > 1 and sset.exchange is not None:
@@ -417,7 +419,6 @@ def run_gpu(args):
             barrier()
             assert torch.equal(ref_all, got_all), "peer-memory exchange and all-reduce disagree"
         n_inliers = int(rec[rank, 121])
-        launches_dev = sset.set.launch_count() - launches0
         if world == 1:
             kern_ms = step_ms
         else:  # kernel-only timing for the roofline (same launch, no exchange)
