@@ -693,6 +693,91 @@ private:
   KdTreeGPU::ConstPtr tree_;
 };
 
+// IntegratedICPFactor_ / IntegratedPointToPlaneICPFactor_ (include/gtsam_points/factors/integrated_icp_factor.hpp:27-145): the
+// kd-tree kernel with M = I (point-to-point) or, with use_point_to_plane, the residual scaled row-wise by the target normal
+// (target_normals: host array, n x 3, caller order).  Neither cloud needs covariances.
+class IntegratedICPFactor : public IntegratedMatchingCostFactorB200 {
+public:
+  using shared_ptr = std::shared_ptr<IntegratedICPFactor>;
+  IntegratedICPFactor(Key target_key, Key source_key, const PointCloudGPU::ConstPtr& target, const PointCloudGPU::ConstPtr& source, const KdTreeGPU::ConstPtr& target_tree,
+                      bool use_point_to_plane = false, const double* target_normals = nullptr)
+  : IntegratedMatchingCostFactorB200(target_key, source_key), target_(target), source_(source), tree_(target_tree), plane_(use_point_to_plane) {
+    init(target_normals);
+  }
+  IntegratedICPFactor(const FixedPose& fixed_target_pose, Key source_key, const PointCloudGPU::ConstPtr& target, const PointCloudGPU::ConstPtr& source,
+                      const KdTreeGPU::ConstPtr& target_tree, bool use_point_to_plane = false, const double* target_normals = nullptr)
+  : IntegratedMatchingCostFactorB200(pose_matrix(fixed_target_pose), source_key), target_(target), source_(source), tree_(target_tree), plane_(use_point_to_plane) {
+    init(target_normals);
+  }
+  // frames of the reference's shape (points as Vector4d arrays); the search tree is built on the device
+  template <typename TargetFrame, typename SourceFrame, typename = decltype(std::declval<const TargetFrame&>().points), typename = decltype(std::declval<const SourceFrame&>().points)>
+  IntegratedICPFactor(Key target_key, Key source_key, const std::shared_ptr<const TargetFrame>& target, const std::shared_ptr<const SourceFrame>& source, Context::Ptr ctx = Context::default_context())
+  : IntegratedICPFactor(target_key, source_key, PointCloudGPU::from_frame(target, ctx), PointCloudGPU::from_frame(source, ctx),
+                        std::make_shared<KdTreeGPU>(reinterpret_cast<const double*>(target->points), 4, target->size(), ctx)) {}
+
+  void print(const std::string& s = "", const KeyFormatter& keyFormatter = &default_key_format) const override {
+    print_keys(s, plane_ ? "IntegratedPointToPlaneICPFactor" : "IntegratedICPFactor", keyFormatter);
+    std::cout << "|target|=" << target_->size() << "pts, |source|=" << source_->size() << "pts" << std::endl;
+  }
+  void set_num_threads(int) {}
+  void set_max_correspondence_distance(double dist) { check(b2_factor_set_max_correspondence_distance(factor_, dist), "b2_factor_set_max_correspondence_distance"); }
+  void set_correspondence_update_tolerance(double angle, double trans) {
+    check(b2_factor_set_correspondence_update_tolerance(factor_, angle, trans), "b2_factor_set_correspondence_update_tolerance");
+  }
+  // NonlinearFactor::clone: a new factor over the same (shared) target, source and search tree
+  FactorBasePtr clone() const override {
+    const double* nrm = normals_.empty() ? nullptr : normals_.data();
+    if (is_binary_) return FactorBasePtr(new IntegratedICPFactor(this->keys()[0], this->keys()[1], target_, source_, tree_, plane_, nrm));
+    IntegratedICPFactor* f = new IntegratedICPFactor(this->keys()[0], this->keys()[0], target_, source_, tree_, plane_, nrm);
+    f->is_binary_ = false;
+    f->fixed_target_pose_ = fixed_target_pose_;
+    f->keys_.erase(f->keys_.begin());
+    return FactorBasePtr(f);
+  }
+
+private:
+  void init(const double* target_normals) {
+    if (!source_ || !target_ || !tree_ || (plane_ && target_normals == nullptr)) {
+      std::cerr << "error: target frame doesn't have required attributes for icp" << std::endl;  // integrated_icp_factor_impl.hpp:36-50
+      abort();
+    }
+    if (plane_) normals_.assign(target_normals, target_normals + 3 * target_->size());  // kept for clone()
+    check(b2_icp_factor_create(source_->context()->get(), target_->handle(), tree_->handle(), source_->handle(), plane_ ? 1 : 0, target_normals, &factor_), "b2_icp_factor_create");
+  }
+  PointCloudGPU::ConstPtr target_, source_;
+  KdTreeGPU::ConstPtr tree_;
+  bool plane_;
+  std::vector<double> normals_;
+};
+
+// estimate_covariances (include/gtsam_points/features/covariance_estimation.hpp:41-66) on the device: k nearest neighbours over a
+// kd-tree built on the spot, neighbourhood covariance, eigenvalues replaced by (1e-3, 1, 1).  Returns n row-major 3x3 matrices.
+inline std::vector<std::array<double, 9>> estimate_covariances(const double* points, int point_stride, std::size_t n, int k_neighbors = 10,
+                                                               Context::Ptr ctx = Context::default_context()) {
+  std::vector<std::array<double, 9>> covs(n);
+  if (n) check(b2_estimate_covariances(ctx->get(), points, point_stride, n, k_neighbors, nullptr, covs[0].data()), "b2_estimate_covariances");
+  return covs;
+}
+
+// merge_frames_gpu (include/gtsam_points/types/gaussian_voxelmap_gpu.hpp:127-150): posed frames (world <- frame) -> one cloud
+// downsampled on a voxel grid laid out in the first frame's coordinates; bit-identical to the CPU merge_frames.
+inline PointCloudGPU::Ptr merge_frames_gpu(const std::vector<Mat4>& poses, const std::vector<PointCloudGPU::ConstPtr>& frames, double downsample_resolution,
+                                           Context::Ptr ctx = Context::default_context()) {
+  if (poses.size() != frames.size() || frames.empty()) throw std::invalid_argument("merge_frames_gpu: one pose per frame, at least one frame");
+  std::vector<double> P;
+  std::vector<const b2_cloud*> handles;
+  std::size_t total = 0;
+  for (std::size_t i = 0; i < frames.size(); i++) {
+    P.insert(P.end(), poses[i].begin(), poses[i].end());
+    handles.push_back(frames[i]->handle());
+    total += frames[i]->size();
+  }
+  std::vector<double> xyz(3 * std::max<std::size_t>(total, 1)), cov(9 * std::max<std::size_t>(total, 1));
+  std::size_t m = 0;
+  check(b2_merge_frames(ctx->get(), P.data(), handles.data(), frames.size(), downsample_resolution, xyz.data(), cov.data(), &m), "b2_merge_frames");
+  return PointCloudGPU::from_packed(xyz.data(), cov.data(), m, ctx);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // NonlinearFactorSet implementation: every device factor of the graph in ONE batched launch
 // (replaces src/gtsam_points/cuda/nonlinear_factor_set_gpu.cpp:48-228; interface optimizers/linearization_hook.hpp:11-29)

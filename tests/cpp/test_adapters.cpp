@@ -133,6 +133,7 @@ int main(int argc, char** argv) {
   const auto exp_vgicp = read_vec(f), exp_gicp = read_vec(f), exp_err = read_vec(f);
   const auto res = read_vec(f);
   const auto exp_unary = read_vec(f), exp_overlap = read_vec(f);
+  const auto exp_icp = read_vec(f), exp_merge = read_vec(f), exp_cov = read_vec(f);  // ICP linearization, merged-frame size, first covariances
   fclose(f);
   const std::size_t nt = tp.size() / 4, ns = sp.size() / 4;
   const double tol = 1e-9;
@@ -284,6 +285,26 @@ int main(int argc, char** argv) {
     voxels_base->save_compact(path);
     auto loaded = GaussianVoxelMapGPU::load(path);
     if (!loaded || loaded->num_voxels() != voxels->num_voxels() || loaded->voxel_resolution() != voxels->voxel_resolution()) fails++;
+  }
+
+  // ---- ICP factor, covariance estimation and merge_frames through the adapters ----
+  {
+    auto icp = std::make_shared<IntegratedICPFactor>(Key(0), Key(1), target_c, source_c);
+    fails += check_against(unpack(icp->linearize(values)), exp_icp, tol);
+    if (icp->num_inliers() != static_cast<int>(exp_icp[121])) fails++;
+    NonlinearFactorSetGPU icp_set;  // an ICP factor batches like any other matching-cost factor
+    if (!icp_set.add(icp)) fails++;
+
+    const auto covs = estimate_covariances(tp.data(), 4, nt, 10);
+    if (covs.size() != nt) fails++;
+    const std::size_t ncheck = std::min<std::size_t>(exp_cov.size() / 9, covs.size());
+    std::size_t close = 0;
+    for (std::size_t i = 0; i < ncheck; i++) close += relerr(covs[i].data(), exp_cov.data() + 9 * i, 9) < 1e-6;
+    if (close + ncheck / 50 < ncheck) fails++;  // the regularised matrix is only as well defined as the normal direction: allow 2 %
+
+    std::vector<Mat4> poses = {pose_matrix(values, 0), pose_matrix(values, 1)};
+    auto merged = merge_frames_gpu(poses, {PointCloudGPU::from_frame(target_c), PointCloudGPU::from_frame(source_c)}, res[0]);
+    if (merged->size() != static_cast<std::size_t>(exp_merge[0]) || !merged->has_covs()) fails++;
   }
 
   printf("%s (%d failed checks, vgicp inliers %d)\n", fails ? "FAIL" : "OK", fails, vgicp->num_inliers());

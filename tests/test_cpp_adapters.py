@@ -67,9 +67,12 @@ def test_adapters_match_oracle_in_reference_call_order(tmp_path, mock_gtsam):
     ev, eg = fv.linearize_raw(d), fg.linearize_raw(d)
     errs = np.array([fv.error(d2), fg.error(d2)])
     overlap = np.array([vm.overlap(osrc, d)])
+    eicp = orc.Factor(otgt, osrc, tree=orc.KdTree(otgt, 4), num_threads=4, icp="point").linearize_raw(d)
+    merged_xyz, _ = orc.merge_frames(np.stack([Tt, Ts]), [otgt, osrc], 0.5)
+    cov_head = orc.estimate_covariances(tp, 10, num_threads=4)[:256]
     case = tmp_path / "case.bin"
     with open(case, "wb") as f:
-        for a in (pad4(tp), pad44(tc), pad4(sp), pad44(sc), Tt, Ts, Ts2, ev, eg, errs, np.array([0.5]), ev, overlap):
+        for a in (pad4(tp), pad44(tc), pad4(sp), pad44(sc), Tt, Ts, Ts2, ev, eg, errs, np.array([0.5]), ev, overlap, eicp, np.array([len(merged_xyz)]), cov_head):
             a = np.ascontiguousarray(a, dtype=np.float64).ravel()
             f.write(np.uint64(a.size).tobytes())
             f.write(a.tobytes())
